@@ -1,0 +1,565 @@
+// gemm.cu — persistent, warp-specialised tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+// One kernel serves every dense contraction of the denoise step that is not attention:
+//   * Linear layers (diffusers Attention.to_q/k/v/out, Transformer2DModel.proj_in/out, FeedForward;
+//     reference adapter projections src/models/attention.py:125-132,157): the 1-tap case.
+//   * 3x3 convolutions of ResnetBlock2D / Upsample2D / conv shortcut: 9 taps,
+//     the A operand is fetched by 4-D TMA boxes over the NHWC activation, shifted per tap; TMA
+//     out-of-bounds zero fill implements the padding=1 halo.
+//   * Stride-2 3x3 convolutions of Downsample2D: the NHWC input is viewed as [N, H/2, 2, W/2, 2C] (5-D)
+//     so every tap is again one dense TMA box.
+//
+// Layout: activations are NHWC bf16 ([rows, C] row-major == K-major A operand), weights are [N, K]
+// row-major bf16 (K-major B operand; for convs K = tap*Cin + c). Accumulation fp32 in TMEM.
+//
+// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer, warps 2..5
+// epilogue (TMEM -> registers -> fused bias / per-image bias / residual / GEGLU -> bf16 -> smem -> TMA store).
+// Persistent: grid = min(#tiles, #SMs); two TMEM accumulator stages so the epilogue of tile i overlaps the
+// main loop of tile i+1.
+#include "tc.cuh"
+#include "host_common.h"
+#include "../../include/mvd_b200.h"
+
+namespace mvd {
+
+constexpr int BM = 128;  // tile rows (output pixels)
+constexpr int BK = 64;   // bf16 elements per k-block = one 128-B swizzle row
+constexpr int EPI_BUFS = 4;
+constexpr int EPI_BUF_BYTES = 32 * 32 * 2;  // 32 rows x 32 bf16
+
+struct GemmArgs {
+  int tiles_total, tiles_n;
+  int tiles_x, tiles_y;  // m-tile -> (x, y, img) with x fastest
+  int TW, TH, TN;        // tile = TN images x TH rows x TW pixels (=128)
+  int bx, by;            // per-epilogue-warp store box (bx * by * bn = 32 pixels)
+  int ntaps;             // 1 (linear / 1x1) or 9 (3x3)
+  int kc_per_tap;        // k-blocks per tap (Cin / 64, both sources)
+  int kc_a1;             // k-blocks per tap that come from source 1 (rest from source 2)
+  int cin;               // Cin: weight K offset of tap t is t * cin
+  int c_s2;              // stride-2 mode: channel count C of the 5-D view (inner dim is 2C)
+  int N;                 // output columns
+  int geglu;             // 1: tile columns are [a | g] halves, out = a * gelu(g), N/2 output columns
+  int has_res;
+  int rows_per_img;      // img index for img_bias: n_coord + x_coord / rows_per_img
+  int img_bias_ld;
+  int img_max;           // clamp for the img index (padded rows of the last tile)
+  const __nv_bfloat16* bias;  // [N] (permuted like the weight rows when geglu)
+  const float* img_bias;      // [imgs, img_bias_ld] fp32 (e.g. time-embedding projection)
+};
+
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 32 KB
+  static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
+  static constexpr int BAR_BYTES = 1024;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
+  static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+template <int BN, bool S2>
+__global__ void __launch_bounds__(192, 1)
+gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
+                 const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
+                 const __grid_constant__ CUtensorMap mapRes, const GemmArgs p) {
+  using L = SmemLayout<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + L::STAGES * L::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + L::EPI_BYTES);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + L::STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * L::STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint64_t* res_bar = tmem_empty + 2;          // [4 warps][EPI_BUFS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * EPI_BUFS);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int k_blocks = p.ntaps * p.kc_per_tap;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapB);
+    tma_prefetch_desc(&mapOut);
+    for (int s = 0; s < L::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    for (int i = 0; i < 4 * EPI_BUFS; ++i) mbar_init(&res_bar[i], 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        const int n_tile = t % p.tiles_n;
+        int m_tile = t / p.tiles_n;
+        const int x0 = (m_tile % p.tiles_x) * p.TW;
+        m_tile /= p.tiles_x;
+        const int y0 = (m_tile % p.tiles_y) * p.TH;
+        const int n0 = (m_tile / p.tiles_y) * p.TN;
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int ky = (p.ntaps == 9) ? tap / 3 : 1;
+          const int kx = (p.ntaps == 9) ? tap % 3 : 1;
+          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * L::STAGE_BYTES;
+            uint8_t* sb = sa + L::A_BYTES;
+            mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+            if constexpr (S2) {
+              // input pixel (2*oy + ky - 1, 2*ox + kx - 1) in the [N, H/2, 2, W/2, 2C] view
+              const int px = (kx == 1) ? 0 : 1, py = (ky == 1) ? 0 : 1;
+              const int wx = x0 + ((kx == 0) ? -1 : 0), hy = y0 + ((ky == 0) ? -1 : 0);
+              tma_load_5d(sa, &mapA, &full[stage], px * p.c_s2 + kc * BK, wx, py, hy, n0);
+            } else {
+              if (kc < p.kc_a1)
+                tma_load_4d(sa, &mapA, &full[stage], kc * BK, x0 + kx - 1, y0 + ky - 1, n0);
+              else
+                tma_load_4d(sa, &mapA2, &full[stage], (kc - p.kc_a1) * BK, x0 + kx - 1, y0 + ky - 1, n0);
+            }
+            tma_load_2d(sb, &mapB, &full[stage], tap * p.cin + kc * BK, n_tile * BN);
+            if (++stage == L::STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * L::ACC_STRIDE;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa);
+          const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
+            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == L::STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    uint8_t* my_smem = epi_smem + q * (EPI_BUFS * EPI_BUF_BYTES);
+    uint64_t* my_res_bar = res_bar + q * EPI_BUFS;
+    const int r0 = q * 32;  // first tile row of this warp
+    // position of this warp's 32-pixel slab inside the tile
+    const int wx_off = r0 % p.TW;
+    const int wy_off = (r0 / p.TW) % p.TH;
+    const int wn_off = r0 / (p.TW * p.TH);
+    // position of this lane's pixel inside the tile (for the per-image bias)
+    const int row = r0 + lane;
+    const int lx = row % p.TW;
+    const int ln = row / (p.TW * p.TH);
+    const int n_chunks = p.geglu ? BN / 64 : BN / 32;
+    const int out_cols_per_tile = p.geglu ? BN / 2 : BN;
+    const int n_out = p.geglu ? p.N / 2 : p.N;
+
+    uint32_t g = 0;  // running chunk counter -> staging buffer + barrier parity
+    int it = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+      const int n_tile = t % p.tiles_n;
+      int m_tile = t / p.tiles_n;
+      const int x0 = (m_tile % p.tiles_x) * p.TW;
+      m_tile /= p.tiles_x;
+      const int y0 = (m_tile % p.tiles_y) * p.TH;
+      const int n0 = (m_tile / p.tiles_y) * p.TN;
+      const int sx = x0 + wx_off, sy = y0 + wy_off, sn = n0 + wn_off;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      const int col_base = n_tile * out_cols_per_tile;
+
+      // prefetch residual slabs for the first two chunks (their buffers are free: at most one store
+      // group from the previous tile may still be reading, and it is neither of these two buffers
+      // after the wait below)
+      if (p.has_res) {
+        if (lane == 0) {
+          tma_store_wait_read0();
+          for (int c = 0; c < 2 && c < n_chunks; ++c) {
+            const uint32_t gb = (g + c) % EPI_BUFS;
+            mbar_arrive_expect_tx(&my_res_bar[gb], EPI_BUF_BYTES);
+            tma_load_4d(my_smem + gb * EPI_BUF_BYTES, &mapRes, &my_res_bar[gb], col_base + c * 32, sx, sy, sn);
+          }
+        }
+        __syncwarp();
+      }
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_acc = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+      int img = ln + n0 + (x0 + lx) / p.rows_per_img;
+      img = img < p.img_max ? img : p.img_max;
+
+      for (int c = 0; c < n_chunks; ++c, ++g) {
+        const uint32_t buf = g % EPI_BUFS;
+        const uint32_t buf_parity = (g / EPI_BUFS) & 1;
+        uint8_t* sbuf = my_smem + buf * EPI_BUF_BYTES;
+        const int col0 = col_base + c * 32;  // first output column of this chunk
+
+        // buffer (g+2)%4 was last stored by chunk g-2: allow only the newest store group to be pending
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          if (p.has_res && c + 2 < n_chunks) {
+            const uint32_t gb = (g + 2) % EPI_BUFS;
+            mbar_arrive_expect_tx(&my_res_bar[gb], EPI_BUF_BYTES);
+            tma_load_4d(my_smem + gb * EPI_BUF_BYTES, &mapRes, &my_res_bar[gb], col0 + 64, sx, sy, sn);
+          }
+        }
+        __syncwarp();
+
+        float v[32];
+        if (!p.geglu) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_acc + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
+          }
+          if (p.img_bias != nullptr) {
+            const float* ib = p.img_bias + static_cast<size_t>(img) * p.img_bias_ld;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += ib[col0 + j];
+          }
+        } else {
+          uint32_t ra[32], rg[32];
+          tmem_ld_32x32b_x32(t_acc + c * 32, ra);
+          tmem_ld_32x32b_x32(t_acc + BN / 2 + c * 32, rg);
+          tmem_ld_wait();
+          const int wa = n_tile * BN + c * 32;  // permuted weight-row index of the 'a' columns
+          const int wg = wa + BN / 2;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float a = __uint_as_float(ra[j]), gt = __uint_as_float(rg[j]);
+            if (p.bias != nullptr) {
+              a += __bfloat162float(p.bias[wa + j]);
+              gt += __bfloat162float(p.bias[wg + j]);
+            }
+            v[j] = a * gelu_erf(gt);
+          }
+        }
+
+        if (p.has_res) {
+          mbar_wait(&my_res_bar[buf], buf_parity);
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(sbuf + lane * 64 + ((ch ^ ((lane >> 1) & 3)) * 16));
+            const float2 f0 = unpack_bf16x2(rv.x), f1 = unpack_bf16x2(rv.y), f2 = unpack_bf16x2(rv.z),
+                         f3 = unpack_bf16x2(rv.w);
+            v[ch * 8 + 0] += f0.x; v[ch * 8 + 1] += f0.y; v[ch * 8 + 2] += f1.x; v[ch * 8 + 3] += f1.y;
+            v[ch * 8 + 4] += f2.x; v[ch * 8 + 5] += f2.y; v[ch * 8 + 6] += f3.x; v[ch * 8 + 7] += f3.y;
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint4 o;
+          o.x = pack_bf16x2(v[ch * 8 + 0], v[ch * 8 + 1]);
+          o.y = pack_bf16x2(v[ch * 8 + 2], v[ch * 8 + 3]);
+          o.z = pack_bf16x2(v[ch * 8 + 4], v[ch * 8 + 5]);
+          o.w = pack_bf16x2(v[ch * 8 + 6], v[ch * 8 + 7]);
+          *reinterpret_cast<uint4*>(sbuf + lane * 64 + ((ch ^ ((lane >> 1) & 3)) * 16)) = o;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (col0 < n_out) tma_store_4d(&mapOut, sbuf, col0, sx, sy, sn);
+          tma_store_commit();
+        }
+      }
+      // accumulator fully read -> hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
+    if (lane == 0) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct ConvGeom {
+  int Nimg, H, W;     // OUTPUT geometry (pixels)
+  int TW, TH, TN;
+};
+
+static void pick_tile(int Nimg, int H, int W, int* TW, int* TH, int* TN) {
+  // 128 output pixels per tile as TN images x TH rows x TW pixels; prefer exact cover along x.
+  int tw = 128;
+  while (tw > 1 && tw > W) tw >>= 1;            // largest power of two <= W (<=128)
+  if (H > 1 && W % tw != 0) {                   // e.g. W = 96 -> 32, 48 -> 16, 24 -> 8, 12 -> 4
+    int cand = tw;
+    while (cand > 1 && W % cand != 0) cand >>= 1;
+    if (cand >= 4) tw = cand;
+  }
+  int rest = 128 / tw;
+  int th = 1;
+  while (th * 2 <= rest && th * 2 <= H) th <<= 1;
+  if (H % th != 0) {
+    int cand = th;
+    while (cand > 1 && H % cand != 0) cand >>= 1;
+    th = cand;
+  }
+  *TW = tw;
+  *TH = th;
+  *TN = 128 / (tw * th);
+  (void)Nimg;
+}
+
+template <int BN, bool S2>
+static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
+                      const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool configured = false;  // benign race: attribute set is idempotent
+  if (!configured) {
+    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  int grid = args.tiles_total < sm_count() ? args.tiles_total : sm_count();
+  gemm_conv_kernel<BN, S2><<<grid, 192, L::TOTAL, stream>>>(mA, mA2, mB, mO, mR, args);
+  MVD_CUDA(cudaGetLastError());
+  return MVD_OK;
+}
+
+static int pick_bn(int N, int M_tiles, bool geglu) {
+  // Candidate tile widths; choose the one with the least padded work, ties -> fewer waves imbalance.
+  const int cands_plain[] = {256, 160, 128, 64};
+  const int cands_geglu[] = {256, 128, 64};
+  const int* cands = geglu ? cands_geglu : cands_plain;
+  const int nc = geglu ? 3 : 4;
+  const int sms = sm_count();
+  int best = 64;
+  double best_cost = 1e30;
+  for (int i = 0; i < nc; ++i) {
+    const int bn = cands[i];
+    const int tn = (N + bn - 1) / bn;
+    const long tiles = static_cast<long>(tn) * M_tiles;
+    const long waves = (tiles + sms - 1) / sms;
+    // cost ~ waves * per-tile time (prop. to bn) ; small fixed per-tile overhead favours larger tiles
+    const double cost = static_cast<double>(waves) * (bn + 24.0);
+    if (cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
+}
+
+// Generic launcher. x: NHWC-like activation described as (C, Wd, Hd, Nd) with element strides.
+struct OperandA {
+  const void* ptr;
+  int C;                 // channels of this source
+  int64_t pix_stride;    // elements between consecutive pixels (>= C)
+};
+
+static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, int64_t ldw, const void* bias,
+                         const float* img_bias, int img_bias_ld, int rows_per_img, const void* residual,
+                         int64_t res_pix_stride, void* out, int64_t out_pix_stride, int Nimg, int H, int W /*output*/,
+                         int Cout, int ntaps, int stride, int geglu, int force_bn, cudaStream_t stream) {
+  const int Cin = a1.C + (a2 ? a2->C : 0);
+  MVD_CHECK(Cin % 64 == 0 && a1.C % 64 == 0, "gemm/conv: K (=%d, first source %d) must be a multiple of 64", Cin,
+            a1.C);
+  MVD_CHECK(Cout % 32 == 0, "gemm/conv: N (=%d) must be a multiple of 32", Cout);
+  MVD_CHECK(!(stride == 2 && (a2 || ntaps != 9)), "stride-2 supports single-source 3x3 only");
+  MVD_CHECK(!geglu || (force_bn > 0 && Cout % force_bn == 0 && !residual && !img_bias),
+            "geglu needs an explicit tile width dividing N, and no residual");
+  MVD_CHECK((reinterpret_cast<uintptr_t>(a1.ptr) & 15) == 0 && (reinterpret_cast<uintptr_t>(w) & 15) == 0 &&
+                (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+            "gemm/conv: pointers must be 16-byte aligned");
+  MVD_CHECK(a1.pix_stride % 8 == 0 && out_pix_stride % 8 == 0 && ldw % 8 == 0,
+            "gemm/conv: strides must be multiples of 8 elements");
+
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  int TW, TH, TN;
+  pick_tile(Nimg, H, W, &TW, &TH, &TN);
+  g.TW = TW; g.TH = TH; g.TN = TN;
+  g.tiles_x = (W + TW - 1) / TW;
+  g.tiles_y = (H + TH - 1) / TH;
+  const int tiles_img = (Nimg + TN - 1) / TN;
+  const int tiles_m = g.tiles_x * g.tiles_y * tiles_img;
+  g.bx = TW < 32 ? TW : 32;
+  g.by = (32 / g.bx) < TH ? (32 / g.bx) : TH;
+  const int bn_img = 32 / (g.bx * g.by);
+  g.ntaps = ntaps;
+  g.kc_per_tap = Cin / 64;
+  g.kc_a1 = a1.C / 64;
+  g.cin = Cin;
+  g.c_s2 = a1.C;
+  g.N = Cout;
+  g.geglu = geglu;
+  g.has_res = residual != nullptr;
+  g.rows_per_img = rows_per_img > 0 ? rows_per_img : (1 << 30);
+  g.img_bias = img_bias;
+  g.img_bias_ld = img_bias_ld;
+  g.img_max = rows_per_img > 0 ? (W - 1) / rows_per_img : Nimg - 1;
+  g.bias = static_cast<const __nv_bfloat16*>(bias);
+
+  const int BN = force_bn > 0 ? force_bn : pick_bn(Cout, tiles_m, geglu != 0);
+  g.tiles_n = (Cout + BN - 1) / BN;
+  g.tiles_total = g.tiles_n * tiles_m;
+
+  CUtensorMap mA, mA2, mB, mO, mR;
+  // --- A maps
+  if (stride == 2) {
+    // input is [Nimg, 2H, 2W, C]; view (2C, W, 2, H, Nimg)
+    const uint64_t ps = static_cast<uint64_t>(a1.pix_stride);
+    const uint64_t dims[5] = {static_cast<uint64_t>(2 * a1.C), static_cast<uint64_t>(W), 2, static_cast<uint64_t>(H),
+                              static_cast<uint64_t>(Nimg)};
+    MVD_CHECK(a1.pix_stride == a1.C, "stride-2 conv needs a dense NHWC input");
+    const uint64_t strides[4] = {2 * ps * 2, 2 * static_cast<uint64_t>(W) * ps * 2,
+                                 2 * 2 * static_cast<uint64_t>(W) * ps * 2,
+                                 static_cast<uint64_t>(2 * H) * 2 * W * ps * 2};
+    const uint32_t box[5] = {64, static_cast<uint32_t>(TW), 1, static_cast<uint32_t>(TH), static_cast<uint32_t>(TN)};
+    if (int e = make_tmap_bf16(&mA, a1.ptr, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+    mA2 = mA;
+  } else {
+    auto mk = [&](CUtensorMap* m, const OperandA& a) -> int {
+      const uint64_t ps = static_cast<uint64_t>(a.pix_stride);
+      const uint64_t dims[4] = {static_cast<uint64_t>(a.C), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                                static_cast<uint64_t>(Nimg)};
+      const uint64_t strides[3] = {ps * 2, static_cast<uint64_t>(W) * ps * 2,
+                                   static_cast<uint64_t>(H) * W * ps * 2};
+      const uint32_t box[4] = {64, static_cast<uint32_t>(TW), static_cast<uint32_t>(TH), static_cast<uint32_t>(TN)};
+      return make_tmap_bf16(m, a.ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    if (int e = mk(&mA, a1)) return e;
+    if (a2) {
+      if (int e = mk(&mA2, *a2)) return e;
+    } else {
+      mA2 = mA;
+    }
+  }
+  // --- B map: [Cout, ntaps*Cin] row-major
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(ntaps) * Cin, static_cast<uint64_t>(Cout)};
+    const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    if (int e = make_tmap_bf16(&mB, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+  }
+  // --- output / residual maps (per-warp slab boxes of 32 pixels x 32 channels, 64-B swizzle)
+  {
+    const int n_out = geglu ? Cout / 2 : Cout;
+    auto mk = [&](CUtensorMap* m, const void* ptr, int64_t pstride) -> int {
+      const uint64_t ps = static_cast<uint64_t>(pstride);
+      const uint64_t dims[4] = {static_cast<uint64_t>(n_out), static_cast<uint64_t>(W), static_cast<uint64_t>(H),
+                                static_cast<uint64_t>(Nimg)};
+      const uint64_t strides[3] = {ps * 2, static_cast<uint64_t>(W) * ps * 2,
+                                   static_cast<uint64_t>(H) * W * ps * 2};
+      const uint32_t box[4] = {32, static_cast<uint32_t>(g.bx), static_cast<uint32_t>(g.by),
+                               static_cast<uint32_t>(bn_img)};
+      return make_tmap_bf16(m, ptr, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
+    if (int e = mk(&mO, out, out_pix_stride)) return e;
+    if (residual) {
+      MVD_CHECK(res_pix_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+                "gemm/conv: residual must be 16-byte aligned with stride %% 8 == 0");
+      if (int e = mk(&mR, residual, res_pix_stride)) return e;
+    } else {
+      mR = mO;
+    }
+  }
+
+#define MVD_LAUNCH_BN(bn)                                                               \
+  case bn:                                                                              \
+    return stride == 2 ? launch_one<bn, true>(mA, mA2, mB, mO, mR, g, stream)           \
+                       : launch_one<bn, false>(mA, mA2, mB, mO, mR, g, stream);
+  switch (BN) {
+    MVD_LAUNCH_BN(64)
+    MVD_LAUNCH_BN(128)
+    MVD_LAUNCH_BN(160)
+    MVD_LAUNCH_BN(256)
+    default:
+      set_error("gemm/conv: unsupported tile width %d", BN);
+      return MVD_ERR_INVALID;
+  }
+#undef MVD_LAUNCH_BN
+}
+
+}  // namespace mvd
+
+extern "C" {
+
+int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
+                    int64_t ldw, const void* bias, const float* row_group_bias, int row_group_bias_ld,
+                    int rows_per_group, const void* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
+                    int geglu, int tile_n, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(M > 0 && N > 0 && k1 > 0, "linear: empty problem M=%d N=%d K=%d", M, N, k1);
+  OperandA s1{a, k1, lda};
+  OperandA s2{a2, k2, lda2};
+  return run_gemm_conv(s1, (a2 && k2 > 0) ? &s2 : nullptr, w, ldw, bias, row_group_bias, row_group_bias_ld,
+                       rows_per_group, residual, ldr, out, ldo, /*Nimg=*/1, /*H=*/1, /*W=*/M, N, /*ntaps=*/1,
+                       /*stride=*/1, geglu, tile_n, static_cast<cudaStream_t>(stream));
+}
+
+int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
+                     const float* img_bias, const void* residual, void* out, int n_img, int h_out, int w_out,
+                     int c_out, int stride, int tile_n, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(n_img > 0 && h_out > 0 && w_out > 0, "conv3x3: empty problem");
+  MVD_CHECK(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
+  OperandA s1{x, cin1, cin1};
+  OperandA s2{x2, cin2, cin2};
+  const int cin = cin1 + ((x2 && cin2 > 0) ? cin2 : 0);
+  return run_gemm_conv(s1, (x2 && cin2 > 0) ? &s2 : nullptr, w, static_cast<int64_t>(9) * cin, bias, img_bias, c_out,
+                       /*rows_per_group=*/0, residual, c_out, out, c_out, n_img, h_out, w_out, c_out, /*ntaps=*/9,
+                       stride, /*geglu=*/0, tile_n, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

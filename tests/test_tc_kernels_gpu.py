@@ -1,0 +1,173 @@
+"""GPU parity of the three tensor-core kernels (GEMM/conv/attention) against fp32 torch math on the same
+bf16 inputs. Tolerances: outputs are bf16 (rel 2^-8); fp32 accumulation. Written in the test below."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _cmp(got, ref, name, atol, rtol=2e-2):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    cos = F.cosine_similarity(got.flatten(), ref.flatten(), dim=0).item()
+    bad = (err > tol).sum().item()
+    print(f"{name}: max_abs={err.max().item():.4e} ref_max={ref.abs().max().item():.3f} cos={cos:.6f} bad={bad}")
+    assert bad == 0 and cos > 0.9995, f"{name}: {bad} elements out of tolerance, cos={cos}"
+
+
+def _randn(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to("cuda", torch.bfloat16)
+
+
+@pytest.mark.parametrize("tile_n", [0, 64, 128, 160, 256])
+@pytest.mark.parametrize("M,N,K", [(1000, 320, 320), (256, 1280, 640), (77, 640, 1024), (4096, 320, 1280)])
+def test_linear_plain(M, N, K, tile_n):
+    from mvd_b200 import ops
+
+    a = _randn(M, K, seed=1)
+    w = _randn(N, K, scale=K ** -0.5, seed=2)
+    out = ops.linear(a, w, tile_n=tile_n)
+    torch.cuda.synchronize()
+    _cmp(out, a.float() @ w.float().t(), f"linear {M}x{N}x{K} bn={tile_n}", atol=2e-2)
+
+
+def test_linear_epilogues():
+    from mvd_b200 import ops
+
+    M, N, K = 2048 + 40, 640, 640
+    a = _randn(M, K, seed=1)
+    w = _randn(N, K, scale=K ** -0.5, seed=2)
+    b = _randn(N, seed=3)
+    r = _randn(M, N, seed=4)
+    ref = a.float() @ w.float().t() + b.float() + r.float()
+    _cmp(ops.linear(a, w, bias=b, residual=r), ref, "linear bias+res", atol=3e-2)
+    # strided views: a is a column slice of a wider matrix, out is a column slice too
+    wide = _randn(M, 3 * K, seed=5)
+    a_v = wide[:, K:2 * K]
+    out_wide = torch.zeros(M, 2 * N, device="cuda", dtype=torch.bfloat16)
+    ops.linear(a_v, w, bias=b, out=out_wide[:, N:])
+    _cmp(out_wide[:, N:], a_v.float() @ w.float().t() + b.float(), "linear strided", atol=3e-2)
+    assert out_wide[:, :N].abs().max().item() == 0
+    # two sources (channel concat)
+    a2 = _randn(M, 320, seed=6)
+    w2 = _randn(N, K + 320, scale=(K + 320) ** -0.5, seed=7)
+    ref = torch.cat([a.float(), a2.float()], 1) @ w2.float().t()
+    _cmp(ops.linear(a, w2, a2=a2), ref, "linear two-source", atol=3e-2)
+    # per-row-group bias (rows_per_group = 512)
+    g = torch.randn(5, N, device="cuda")
+    ref = a.float() @ w.float().t() + g[(torch.arange(M, device="cuda") // 512)]
+    _cmp(ops.linear(a, w, row_group_bias=g, rows_per_group=512), ref, "linear group-bias", atol=3e-2)
+
+
+@pytest.mark.parametrize("tile_n", [128, 256])
+def test_linear_geglu(tile_n):
+    from mvd_b200 import ops
+
+    M, C = 1024 + 8, 320
+    a = _randn(M, C, seed=1)
+    w = _randn(8 * C, C, scale=C ** -0.5, seed=2)   # rows [0,4C) = value, [4C,8C) = gate
+    b = _randn(8 * C, seed=3)
+    h = a.float() @ w.float().t() + b.float()
+    ref = h[:, :4 * C] * F.gelu(h[:, 4 * C:])
+    half = tile_n // 2
+    # interleave [value block | gate block] per tile
+    wv, wg = w[:4 * C].view(-1, half, C), w[4 * C:].view(-1, half, C)
+    wp = torch.cat([wv, wg], 1).reshape(8 * C, C).contiguous()
+    bp = torch.cat([b[:4 * C].view(-1, half), b[4 * C:].view(-1, half)], 1).reshape(-1).contiguous()
+    out = ops.linear(a, wp, bias=bp, geglu=True, tile_n=tile_n)
+    _cmp(out, ref, f"geglu bn={tile_n}", atol=3e-2)
+
+
+def _conv_ref(x, w9, bias, img_bias, residual, stride, x2=None):
+    xin = x.float() if x2 is None else torch.cat([x.float(), x2.float()], -1)
+    cin = xin.shape[-1]
+    cout = w9.shape[0]
+    w = w9.float().view(cout, 3, 3, cin).permute(0, 3, 1, 2)
+    y = F.conv2d(xin.permute(0, 3, 1, 2), w, bias=None if bias is None else bias.float(), stride=stride, padding=1)
+    y = y.permute(0, 2, 3, 1)
+    if img_bias is not None:
+        y = y + img_bias[:, None, None, :]
+    if residual is not None:
+        y = y + residual.float()
+    return y
+
+
+@pytest.mark.parametrize("n,h,w,cin,cout", [(2, 16, 16, 64, 64), (2, 64, 64, 320, 320), (3, 8, 8, 1280, 1280),
+                                             (1, 32, 32, 640, 320), (2, 24, 24, 128, 64), (1, 96, 96, 64, 64),
+                                             (5, 12, 12, 64, 96)])
+def test_conv3x3(n, h, w, cin, cout):
+    from mvd_b200 import ops
+
+    x = _randn(n, h, w, cin, seed=1)
+    w9 = _randn(cout, 9 * cin, scale=(9 * cin) ** -0.5, seed=2)
+    b = _randn(cout, seed=3)
+    ib = torch.randn(n, cout, device="cuda")
+    r = _randn(n, h, w, cout, seed=4)
+    _cmp(ops.conv3x3(x, w9), _conv_ref(x, w9, None, None, None, 1), f"conv {n}x{h}x{w} {cin}->{cout}", atol=3e-2)
+    _cmp(ops.conv3x3(x, w9, bias=b, img_bias=ib, residual=r), _conv_ref(x, w9, b, ib, r, 1),
+         f"conv+epi {n}x{h}x{w} {cin}->{cout}", atol=4e-2)
+
+
+@pytest.mark.parametrize("n,h,w,c", [(2, 64, 64, 320), (3, 16, 16, 1280), (1, 32, 32, 640), (2, 24, 24, 64)])
+def test_conv3x3_stride2(n, h, w, c):
+    from mvd_b200 import ops
+
+    x = _randn(n, h, w, c, seed=1)
+    w9 = _randn(c, 9 * c, scale=(9 * c) ** -0.5, seed=2)
+    b = _randn(c, seed=3)
+    _cmp(ops.conv3x3(x, w9, bias=b, stride=2), _conv_ref(x, w9, b, None, None, 2), f"conv s2 {n}x{h}x{w} {c}",
+         atol=3e-2)
+
+
+def test_conv3x3_two_source():
+    from mvd_b200 import ops
+
+    x = _randn(2, 32, 32, 640, seed=1)
+    x2 = _randn(2, 32, 32, 320, seed=5)
+    w9 = _randn(640, 9 * 960, scale=(9 * 960) ** -0.5, seed=2)
+    _cmp(ops.conv3x3(x, w9, x2=x2), _conv_ref(x, w9, None, None, None, 1, x2=x2), "conv two-source", atol=3e-2)
+
+
+def _attn_ref(q, k, v, heads, scale):
+    B, Sq, C = q.shape
+    qh = q.float().view(B, Sq, heads, 64).transpose(1, 2)
+    kh = k.float().view(B, -1, heads, 64).transpose(1, 2)
+    vh = v.float().view(B, -1, heads, 64).transpose(1, 2)
+    o = F.scaled_dot_product_attention(qh, kh, vh, scale=scale)
+    return o.transpose(1, 2).reshape(B, Sq, C)
+
+
+@pytest.mark.parametrize("B,heads,Sq,Skv", [(2, 5, 256, 256), (2, 20, 64, 77), (1, 10, 200, 1000), (4, 5, 4096, 4096),
+                                             (1, 5, 1024, 4 * 1024), (8, 20, 64, 64)])
+@pytest.mark.parametrize("qscale", [1.0, 6.0])
+def test_attention(B, heads, Sq, Skv, qscale):
+    from mvd_b200 import ops
+
+    C = heads * 64
+    q = _randn(B, Sq, C, scale=qscale, seed=1)
+    k = _randn(B, Skv, C, seed=2)
+    v = _randn(B, Skv, C, seed=3)
+    out = ops.attention(q, k, v, heads)
+    torch.cuda.synchronize()
+    _cmp(out, _attn_ref(q, k, v, heads, 0.125), f"attn B{B} h{heads} {Sq}x{Skv} qs{qscale}", atol=1.5e-2)
+
+
+def test_attention_strided_fused_qkv():
+    """q/k/v as column slices of one fused projection output, out written into a slice of a wider buffer."""
+    from mvd_b200 import ops
+
+    B, S, heads = 2, 384, 5
+    C = heads * 64
+    qkv = _randn(B, S, 3 * C, seed=1)
+    q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    cat = torch.zeros(B, S, 2 * C, device="cuda", dtype=torch.bfloat16)
+    ops.attention(q, k, v, heads, out=cat[:, :, C:])
+    _cmp(cat[:, :, C:], _attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), heads, 0.125), "attn strided",
+         atol=1.5e-2)
+    assert cat[:, :, :C].abs().max().item() == 0
