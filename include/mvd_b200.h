@@ -71,6 +71,86 @@ int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_stride, const
                        int64_t ldo, int64_t o_batch_stride, int batch, int heads, int s_q, int s_kv, float scale,
                        void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Bandwidth-bound normalisation kernels, csrc/norm.cu
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* GroupNorm(groups, eps)(+SiLU) over NHWC bf16 [n_img, hw, c1(+c2)]; x2 (optional) is channel-concatenated after
+ * x1 (fuses torch.cat of the up-path skip connection). out is dense [n_img, hw, c1+c2].
+ * Replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm (eps 1e-6, no SiLU) and
+ * UNet2DConditionModel.conv_norm_out + conv_act. workspace: fp32 scratch of
+ * mvd_groupnorm_workspace_floats() elements. */
+int64_t mvd_groupnorm_workspace_floats(int n_img, int hw, int groups);
+int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const void* gamma, const void* beta, void* out,
+                       int n_img, int hw, int groups, float eps, int silu, float* workspace, int64_t workspace_floats,
+                       void* stream);
+
+/* LayerNorm over the last dim of bf16 [M, C] (BasicTransformerBlock.norm1/2/3) / of small fp32 rows with
+ * optional SiLU (CameraEncoder MLPs, src/models/camera_encoder.py:31-76,81-85). gamma/beta bf16. */
+int mvd_layernorm_bf16(const void* x, int64_t ldx, const void* gamma, const void* beta, void* out, int64_t ldo, int M,
+                       int C, float eps, void* stream);
+int mvd_layernorm_f32(const float* x, const void* gamma, const void* beta, float* out, int M, int C, float eps,
+                      int silu, void* stream);
+
+/* Reference-feature normalisation, src/models/attention.py:95-103:
+ *   out = (x - mean) / clamp(std_unbiased, 1e-6) * 0.5, statistics over dims (0,1) of the RAW reference tensor.
+ * x/out: bf16 [batch, seq, channels] (channels-last). per_pixel=1: the reference tensor was 4-D [B,C,H,W] ->
+ * statistics per pixel over (batch, channel); per_pixel=0: it was 3-D [B,S,C] -> per channel over (batch, seq). */
+int64_t mvd_refnorm_workspace_floats(int channels);
+int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels, int per_pixel, float* workspace,
+                     int64_t workspace_floats, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Elementwise / embedding / layout kernels, csrc/elementwise.cu
+ * ------------------------------------------------------------------------------------------------------- */
+
+/* Camera FiLM, src/models/camera_encoder.py:221-234 (hooked at src/models/mvd_unet.py:354-385):
+ *   out = x * (2*sigmoid(mod[:, :C])*strength) + mod[:, C:]*strength; mod fp32 [n_cam, 2C]; image n uses
+ *   camera n % n_cam. x/out NHWC bf16 [n_img, hw, C] (in place allowed). */
+int mvd_film_bf16(const void* x, void* out, const float* mod, int n_img, int n_cam, int hw, int channels,
+                  float strength, void* stream);
+
+/* out[M,N] = act_out(act_in(x[M,K]) @ w[N,K]^T + bias), M <= 16, fp32 activations, bf16 weights.
+ * TimestepEmbedding, ResnetBlock2D.time_emb_proj (all blocks in one call), CameraEncoder MLPs and modulators
+ * (src/models/camera_encoder.py:31-76,81-88,185-194,221). */
+int mvd_small_linear_f32(const float* x, int64_t ldx, const void* w, const void* bias, float* out, int64_t ldo, int M,
+                         int N, int K, int silu_in, int silu_out, void* stream);
+
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t f) | sin(t f)], fp32. */
+int mvd_timestep_embedding_f32(const float* timesteps, int n_timesteps, float* out, int batch, int dim, void* stream);
+
+/* CameraEncoder.compute_relative_transform + the sinusoidal part of positional_encoding
+ * (src/models/camera_encoder.py:107-120,137-151). cams fp32 [V,3,4]; r_flat [V,9]; t_enc [V, 6*pos_enc_dim]. */
+int mvd_camera_front_f32(const float* source_cam, const float* target_cam, float* r_flat, float* t_enc, int n_views,
+                         int pos_enc_dim, float max_freq, void* stream);
+
+/* UNet conv_in (Conv2d(4,Cout,3,p=1)) on fp32 NCHW latents -> NHWC bf16, with the input-latent FiLM of
+ * src/models/mvd_unet.py:256-258 (mod fp32 [n_cam, 8] or NULL) and the CFG duplication of
+ * src/models/pipeline.py:141 (image n reads latent n % n_latents) folded in. w: [Cout,3,3,4]. */
+int mvd_conv_in_f32_bf16(const float* latents, int n_latents, const float* mod, int n_cam, float strength,
+                         const void* w, const void* bias, void* out, int n_img, int h, int wdt, int c_out,
+                         void* stream);
+
+/* UNet conv_out (Conv2d(Cin,4,3,p=1)) on NHWC bf16 -> fp32 NCHW [n_img,4,h,w]. w: [4,3,3,Cin]. */
+int mvd_conv_out_bf16_f32(const void* x, const void* w, const void* bias, float* out, int n_img, int h, int wdt,
+                          int c_in, void* stream);
+
+/* F.interpolate(scale_factor=2, mode="nearest") of diffusers Upsample2D, NHWC bf16. */
+int mvd_upsample_nearest2x_bf16(const void* x, void* out, int n_img, int h, int wdt, int channels, void* stream);
+
+int mvd_add_bf16(const void* a, const void* b, void* out, int64_t n, void* stream);
+int mvd_cast_f32_bf16(const float* x, void* out, int64_t n, void* stream);
+/* x: [batch, rows, cols] -> out: [batch, cols, rows]; dtype codes 0 = fp32, 1 = bf16 (NCHW <-> NHWC). */
+int mvd_transpose_batched(const void* x, void* out, int batch, int rows, int cols, int src_dtype, int dst_dtype,
+                          void* stream);
+
+/* CFG combine + DDPM v-prediction step, src/models/pipeline.py:156-158,161 (diffusers DDPMScheduler.step):
+ *   v = v_u + g (v_c - v_u); x0 = sqrt_abar*x - sqrt_1m_abar*v; x <- coef_x0*x0 + coef_xt*x + sigma*noise.
+ * model_out fp32 [cfg*n]; latents fp32 [n] updated in place; noise fp32 [n] or NULL. */
+int mvd_cfg_ddpm_step_f32(const float* model_out, float* latents, const float* noise, int64_t n, int cfg,
+                          float guidance, float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float coef_x0,
+                          float coef_xt, float sigma, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

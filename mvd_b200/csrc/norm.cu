@@ -1,0 +1,452 @@
+// norm.cu — bandwidth-bound normalisation kernels (coalesced 128-bit HBM access, warp-shuffle reductions).
+//
+//  * GroupNorm(32)(+SiLU) over NHWC bf16, optionally over the channel concatenation of two tensors
+//    (diffusers ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out).
+//    Two launches: per-(image, row-chunk) partial sums -> apply (which first reduces the partials).
+//  * LayerNorm over the last dim of [M, C] bf16 (BasicTransformerBlock.norm1/2/3) and of small fp32 rows
+//    (CameraEncoder MLPs, src/models/camera_encoder.py:31-76).
+//  * Reference-feature normalisation of src/models/attention.py:95-103: (r - mean) / clamp(std, 1e-6) * 0.5 with
+//    statistics over dims (0,1) of the RAW tensor: per pixel over (batch, channel) for 4-D [B,C,H,W] features,
+//    per channel over (batch, sequence) for 3-D [B,S,C] features; unbiased std.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "host_common.h"
+#include "../../include/mvd_b200.h"
+
+namespace mvd {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_VEC_PER_THREAD = 2;  // C <= 256 * 2 * 8 = 4096
+constexpr int GN_MAX_GROUPS = 32;
+
+__host__ __device__ inline int gn_chunks(int hw) {
+  int c = hw / 64;
+  return c < 1 ? 1 : (c > 64 ? 64 : c);
+}
+
+// partial[n][chunk][g][2] = (sum, sumsq) over the chunk's rows
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
+                int groups, float* __restrict__ partial) {
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
+  const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
+  __shared__ float s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
+  if (threadIdx.x < GN_MAX_GROUPS) {
+    s_sum[threadIdx.x] = 0.f;
+    s_sq[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const int nvec = C / 8;
+#pragma unroll
+  for (int i = 0; i < GN_MAX_VEC_PER_THREAD; ++i) {
+    const int v = threadIdx.x + i * GN_THREADS;
+    if (v >= nvec) break;
+    const int c = v * 8;
+    const __nv_bfloat16* base;
+    int cs, cc;
+    if (c < c1) { base = x1; cs = c1; cc = c; } else { base = x2; cs = c2; cc = c - c1; }
+    base += static_cast<int64_t>(n) * hw * cs + cc;
+    float sum[8], sq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum[k] = sq[k] = 0.f;
+    for (int r = r0; r < r1; ++r) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(r) * cs);
+      float f[8];
+      unpack8(raw, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        sum[k] += f[k];
+        sq[k] += f[k] * f[k];
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int g = (c + k) / cpg;
+      atomicAdd(&s_sum[g], sum[k]);
+      atomicAdd(&s_sq[g], sq[k]);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    float* p = partial + ((static_cast<int64_t>(n) * nchunks + chunk) * groups + threadIdx.x) * 2;
+    p[0] = s_sum[threadIdx.x];
+    p[1] = s_sq[threadIdx.x];
+  }
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
+                int groups, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
+                const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks,
+                __nv_bfloat16* __restrict__ out) {
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
+  const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
+  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
+  if (threadIdx.x < groups) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < stat_chunks; ++k) {
+      const float* p = partial + ((static_cast<int64_t>(n) * stat_chunks + k) * groups + threadIdx.x) * 2;
+      s += p[0];
+      q += p[1];
+    }
+    const double cnt = static_cast<double>(hw) * cpg;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;  // biased variance, as torch GroupNorm
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  }
+  __syncthreads();
+  const int nvec = C / 8;
+#pragma unroll
+  for (int i = 0; i < GN_MAX_VEC_PER_THREAD; ++i) {
+    const int v = threadIdx.x + i * GN_THREADS;
+    if (v >= nvec) break;
+    const int c = v * 8;
+    const __nv_bfloat16* base;
+    int cs, cc;
+    if (c < c1) { base = x1; cs = c1; cc = c; } else { base = x2; cs = c2; cc = c - c1; }
+    base += static_cast<int64_t>(n) * hw * cs + cc;
+    __nv_bfloat16* obase = out + static_cast<int64_t>(n) * hw * C + c;
+    float a[8], b[8];
+    {
+      float gm[8], bt[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + c), gm);
+      unpack8(*reinterpret_cast<const uint4*>(beta + c), bt);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int g = (c + k) / cpg;
+        a[k] = gm[k] * s_rstd[g];
+        b[k] = bt[k] - s_mean[g] * a[k];
+      }
+    }
+    for (int r = r0; r < r1; ++r) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(base + static_cast<int64_t>(r) * cs), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        f[k] = f[k] * a[k] + b[k];
+        if (silu) f[k] = silu_f(f[k]);
+      }
+      *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r) * C) = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, row held in registers, two-pass (exact mean, then centered variance)
+// ------------------------------------------------------------------------------------------------
+template <int VPL>  // 16-byte vectors per lane: C = 32 * 8 * VPL at most
+__global__ void __launch_bounds__(256)
+layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gamma,
+                      const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out, int64_t ldo, int M,
+                      int C, float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int nvec = C / 8;
+  float f[VPL][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      unpack8(*reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + v * 8), f[i]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[i][k];
+    }
+  }
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = f[i][k] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float gm[8], bt[8], o[8];
+      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
+      unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o[k] = (f[i][k] - mean) * rstd * gm[k] + bt[k];
+      *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + v * 8) = pack8(o);
+    }
+  }
+}
+
+// small fp32 rows (camera encoder): one warp per row, any C
+__global__ void layernorm_f32_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                                     const __nv_bfloat16* __restrict__ beta, float* __restrict__ out, int M, int C,
+                                     float eps, int silu) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xr = x + static_cast<int64_t>(row) * C;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += xr[c];
+  const float mean = warp_sum(s) / C;
+  float q = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float d = xr[c] - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+  for (int c = lane; c < C; c += 32) {
+    float v = (xr[c] - mean) * rstd * __bfloat162float(gamma[c]) + __bfloat162float(beta[c]);
+    if (silu) v = silu_f(v);
+    out[static_cast<int64_t>(row) * C + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reference-feature normalisation (src/models/attention.py:95-103)
+// ------------------------------------------------------------------------------------------------
+// mode "pixel": x is NHWC [B, HW, C]; statistics per pixel over (B, C). One warp per pixel.
+__global__ void __launch_bounds__(256)
+refnorm_pixel_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int B, int HW, int C) {
+  const int pix = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (pix >= HW) return;
+  const int nvec = C / 8;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const __nv_bfloat16* r = x + (static_cast<int64_t>(b) * HW + pix) * C;
+    for (int v = lane; v < nvec; v += 32) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(r + v * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += f[k];
+    }
+  }
+  const float cnt = static_cast<float>(B) * C;
+  const float mean = warp_sum(s) / cnt;
+  float q = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const __nv_bfloat16* r = x + (static_cast<int64_t>(b) * HW + pix) * C;
+    for (int v = lane; v < nvec; v += 32) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(r + v * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float d = f[k] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float stdv = fmaxf(sqrtf(warp_sum(q) / (cnt - 1.f)), 1e-6f);  // unbiased, clamped
+  const float scale = 0.5f / stdv;
+  for (int b = 0; b < B; ++b) {
+    const int64_t off = (static_cast<int64_t>(b) * HW + pix) * C;
+    for (int v = lane; v < nvec; v += 32) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + off + v * 8), f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean) * scale;
+      *reinterpret_cast<uint4*>(out + off + v * 8) = pack8(f);
+    }
+  }
+}
+
+// mode "channel": x is [B, S, C] (== [B*S, C]); statistics per channel over all B*S rows.
+// pass 1: per-chunk column sums -> pass 2: means, per-chunk centered sums of squares -> pass 3: apply.
+constexpr int RN_CHUNKS = 64;
+__global__ void __launch_bounds__(256)
+refnorm_col_sum_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C, const float* __restrict__ mean_in,
+                       float* __restrict__ partial /*[chunks][C]*/) {
+  const int c = (blockIdx.y * blockDim.x + threadIdx.x) * 8;
+  if (c >= C) return;
+  const int chunk = blockIdx.x, nchunks = gridDim.x;
+  const int64_t r0 = rows * chunk / nchunks, r1 = rows * (chunk + 1) / nchunks;
+  float m[8], acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    m[k] = mean_in ? mean_in[c + k] : 0.f;
+    acc[k] = 0.f;
+  }
+  for (int64_t r = r0; r < r1; ++r) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + r * C + c), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = f[k] - m[k];
+      acc[k] += mean_in ? d * d : d;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) partial[static_cast<int64_t>(chunk) * C + c + k] = acc[k];
+}
+// reduce partial[chunks][C] -> out[C] = f(sum): mode 0: mean = sum / rows ; mode 1: 0.5 / clamp(sqrt(sum/(rows-1)))
+__global__ void refnorm_col_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double rows, int mode,
+                                            float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0;
+  for (int k = 0; k < chunks; ++k) s += partial[static_cast<int64_t>(k) * C + c];
+  if (mode == 0) {
+    out[c] = static_cast<float>(s / rows);
+  } else {
+    const float stdv = fmaxf(static_cast<float>(sqrt(s / (rows - 1.0))), 1e-6f);
+    out[c] = 0.5f / stdv;
+  }
+}
+__global__ void __launch_bounds__(256)
+refnorm_col_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int64_t nvec_total,
+                         int C, const float* __restrict__ mean, const float* __restrict__ scale) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= nvec_total) return;
+  const int c = static_cast<int>((i * 8) % C);
+  float f[8];
+  unpack8(*reinterpret_cast<const uint4*>(x + i * 8), f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) f[k] = (f[k] - mean[c + k]) * scale[c + k];
+  *reinterpret_cast<uint4*>(out + i * 8) = pack8(f);
+}
+
+}  // namespace mvd
+
+extern "C" {
+
+int64_t mvd_groupnorm_workspace_floats(int n_img, int hw, int groups) {
+  return static_cast<int64_t>(n_img) * mvd::gn_chunks(hw) * groups * 2;
+}
+
+int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const void* gamma, const void* beta, void* out,
+                       int n_img, int hw, int groups, float eps, int silu, float* workspace, int64_t workspace_floats,
+                       void* stream) {
+  using namespace mvd;
+  const int C = c1 + ((x2 != nullptr) ? c2 : 0);
+  if (x2 == nullptr) c2 = 0;
+  MVD_CHECK(n_img > 0 && hw > 0, "groupnorm: empty problem");
+  MVD_CHECK(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "groupnorm: groups=%d C=%d unsupported", groups, C);
+  MVD_CHECK(c1 % 8 == 0 && c2 % 8 == 0 && C / 8 <= GN_THREADS * GN_MAX_VEC_PER_THREAD,
+            "groupnorm: channel counts must be multiples of 8 and C <= 4096 (C=%d)", C);
+  MVD_CHECK(workspace_floats >= mvd_groupnorm_workspace_floats(n_img, hw, groups), "groupnorm: workspace too small");
+  const int chunks = gn_chunks(hw);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  gn_stats_kernel<<<dim3(chunks, n_img), GN_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), c1,
+                                                              static_cast<const __nv_bfloat16*>(x2), c2, hw, groups,
+                                                              workspace);
+  MVD_CUDA(cudaGetLastError());
+  gn_apply_kernel<<<dim3(chunks, n_img), GN_THREADS, 0, st>>>(
+      static_cast<const __nv_bfloat16*>(x1), c1, static_cast<const __nv_bfloat16*>(x2), c2, hw, groups, eps, silu,
+      static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), workspace, chunks,
+      static_cast<__nv_bfloat16*>(out));
+  MVD_CUDA(cudaGetLastError());
+  return MVD_OK;
+}
+
+int mvd_layernorm_bf16(const void* x, int64_t ldx, const void* gamma, const void* beta, void* out, int64_t ldo, int M,
+                       int C, float eps, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(M > 0 && C > 0 && C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldo % 8 == 0,
+            "layernorm: C (=%d) must be a multiple of 8 and <= 2048, strides multiples of 8", C);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = (M + 7) / 8;
+  const int vpl = (C / 8 + 31) / 32;
+  auto xx = static_cast<const __nv_bfloat16*>(x);
+  auto g = static_cast<const __nv_bfloat16*>(gamma);
+  auto b = static_cast<const __nv_bfloat16*>(beta);
+  auto o = static_cast<__nv_bfloat16*>(out);
+  if (vpl <= 2)
+    layernorm_bf16_kernel<2><<<blocks, 256, 0, st>>>(xx, ldx, g, b, o, ldo, M, C, eps);
+  else if (vpl <= 5)
+    layernorm_bf16_kernel<5><<<blocks, 256, 0, st>>>(xx, ldx, g, b, o, ldo, M, C, eps);
+  else
+    layernorm_bf16_kernel<8><<<blocks, 256, 0, st>>>(xx, ldx, g, b, o, ldo, M, C, eps);
+  MVD_CUDA(cudaGetLastError());
+  return MVD_OK;
+}
+
+int mvd_layernorm_f32(const float* x, const void* gamma, const void* beta, float* out, int M, int C, float eps,
+                      int silu, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(M > 0 && C > 0, "layernorm_f32: empty problem");
+  layernorm_f32_kernel<<<(M + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), out, M, C, eps, silu);
+  MVD_CUDA(cudaGetLastError());
+  return MVD_OK;
+}
+
+int64_t mvd_refnorm_workspace_floats(int channels) { return static_cast<int64_t>(mvd::RN_CHUNKS + 2) * channels; }
+
+int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels, int per_pixel, float* workspace,
+                     int64_t workspace_floats, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(batch > 0 && seq > 0 && channels > 0 && channels % 8 == 0, "refnorm: bad shape B=%d S=%d C=%d", batch, seq,
+            channels);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto xx = static_cast<const __nv_bfloat16*>(x);
+  auto oo = static_cast<__nv_bfloat16*>(out);
+  if (per_pixel) {
+    MVD_CHECK(static_cast<int64_t>(batch) * channels > 1, "refnorm: unbiased std needs more than one element");
+    refnorm_pixel_kernel<<<(seq + 7) / 8, 256, 0, st>>>(xx, oo, batch, seq, channels);
+    MVD_CUDA(cudaGetLastError());
+    return MVD_OK;
+  }
+  MVD_CHECK(workspace_floats >= mvd_refnorm_workspace_floats(channels), "refnorm: workspace too small");
+  const int64_t rows = static_cast<int64_t>(batch) * seq;
+  MVD_CHECK(rows > 1, "refnorm: unbiased std needs more than one row");
+  const int chunks = rows < RN_CHUNKS ? static_cast<int>(rows) : RN_CHUNKS;
+  float* partial = workspace;
+  float* mean = workspace + static_cast<int64_t>(RN_CHUNKS) * channels;
+  float* scale = mean + channels;
+  const int tx = 64;
+  dim3 grid(chunks, (channels / 8 + tx - 1) / tx);
+  refnorm_col_sum_kernel<<<grid, tx, 0, st>>>(xx, rows, channels, nullptr, partial);
+  refnorm_col_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(partial, chunks, channels,
+                                                                      static_cast<double>(rows), 0, mean);
+  refnorm_col_sum_kernel<<<grid, tx, 0, st>>>(xx, rows, channels, mean, partial);
+  refnorm_col_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(partial, chunks, channels,
+                                                                      static_cast<double>(rows), 1, scale);
+  const int64_t nvec = rows * channels / 8;
+  refnorm_col_apply_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, st>>>(xx, oo, nvec, channels, mean,
+                                                                                      scale);
+  MVD_CUDA(cudaGetLastError());
+  return MVD_OK;
+}
+
+}  // extern "C"

@@ -171,3 +171,237 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
         "mvd_attention_bf16",
     )
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------
+# bandwidth-bound kernels
+# ----------------------------------------------------------------------------------------------------------
+F32 = torch.float32
+_workspaces: dict = {}
+
+
+def _workspace(device, nfloats: int, tag: str = "ws") -> torch.Tensor:
+    """Persistent fp32 scratch per (device, tag) — stable addresses, CUDA-graph friendly."""
+    key = (str(device), tag)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nfloats:
+        ws = torch.empty(max(nfloats, 1 << 16), device=device, dtype=F32)
+        _workspaces[key] = ws
+    return ws
+
+
+def _contig(t: torch.Tensor, name: str, dtype=BF16):
+    _req(t, name, dtype)
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+
+
+def groupnorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, groups: int = 32, eps: float = 1e-5,
+              silu: bool = False, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: NHWC [N,H,W,C1] or [N,HW,C1] (x2 concatenated along C); returns a dense tensor of x's rank."""
+    _contig(x, "x")
+    n, c1 = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * c1)
+    c2 = 0
+    if x2 is not None:
+        _contig(x2, "x2")
+        c2 = x2.shape[-1]
+        if x2.shape[:-1] != x.shape[:-1]:
+            raise ValueError("x2 must match x except for channels")
+    _contig(gamma, "gamma")
+    _contig(beta, "beta")
+    if gamma.numel() != c1 + c2 or beta.numel() != c1 + c2:
+        raise ValueError("gamma/beta size mismatch")
+    if out is None:
+        out = torch.empty(tuple(x.shape[:-1]) + (c1 + c2,), device=x.device, dtype=BF16)
+    _contig(out, "out")
+    need = lib().mvd_groupnorm_workspace_floats(n, hw, groups)
+    ws = _workspace(x.device, need, "gn")
+    check(
+        lib().mvd_groupnorm_bf16(_p(x), c1, _p(x2), c2, _p(gamma), _p(beta), _p(out), n, hw, groups, float(eps),
+                                 int(silu), _p(ws), ws.numel(), _stream()),
+        "mvd_groupnorm_bf16",
+    )
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: [..., C] bf16 with dense rows; LayerNorm over C."""
+    _req(x, "x")
+    C = x.shape[-1]
+    x2d = x.reshape(-1, C)
+    px, ldx, M, _ = _rows2d(x2d, "x")
+    if out is None:
+        out = torch.empty_like(x2d)
+    o2d = out.reshape(-1, C)
+    po, ldo, _, _ = _rows2d(o2d, "out")
+    check(lib().mvd_layernorm_bf16(px, ldx, _p(gamma), _p(beta), po, ldo, M, C, float(eps), _stream()),
+          "mvd_layernorm_bf16")
+    return out.view(x.shape)
+
+
+def layernorm_f32(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                  silu: bool = False) -> torch.Tensor:
+    _contig(x, "x", F32)
+    M, C = x.shape
+    out = torch.empty_like(x)
+    check(lib().mvd_layernorm_f32(_p(x), _p(gamma), _p(beta), _p(out), M, C, float(eps), int(silu), _stream()),
+          "mvd_layernorm_f32")
+    return out
+
+
+def refnorm(x: torch.Tensor, per_pixel: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: bf16 [B,S,C] channels-last reference features -> normalised (attention.py:95-103 semantics)."""
+    _contig(x, "x")
+    B, S, C = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    need = lib().mvd_refnorm_workspace_floats(C)
+    ws = _workspace(x.device, need, "refnorm")
+    check(lib().mvd_refnorm_bf16(_p(x), _p(out), B, S, C, int(per_pixel), _p(ws), ws.numel(), _stream()),
+          "mvd_refnorm_bf16")
+    return out
+
+
+def film(x: torch.Tensor, mod: torch.Tensor, strength: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: NHWC bf16 [N,...,C]; mod: fp32 [V, 2C]."""
+    _contig(x, "x")
+    _contig(mod, "mod", F32)
+    n, C = x.shape[0], x.shape[-1]
+    hw = x.numel() // (n * C)
+    V = mod.shape[0]
+    if mod.shape[1] != 2 * C:
+        raise ValueError("mod must be [V, 2C]")
+    if n % V != 0:
+        raise ValueError(f"batch {n} is not a multiple of the number of cameras {V}")
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().mvd_film_bf16(_p(x), _p(out), _p(mod), n, V, hw, C, float(strength), _stream()), "mvd_film_bf16")
+    return out
+
+
+def small_linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, silu_in: bool = False,
+                 silu_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: fp32 [M<=16, K]; w: bf16 [N,K]; returns fp32 [M,N]."""
+    _req(x, "x", F32)
+    _contig(w, "w")
+    px, ldx, M, K = _rows2d(x, "x")
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError("inner dimension mismatch")
+    if out is None:
+        out = torch.empty((M, N), device=x.device, dtype=F32)
+    po, ldo, _, _ = _rows2d(out, "out")
+    check(lib().mvd_small_linear_f32(px, ldx, _p(w), _p(bias), po, ldo, M, N, K, int(silu_in), int(silu_out),
+                                     _stream()), "mvd_small_linear_f32")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, batch: int, dim: int = 320) -> torch.Tensor:
+    _contig(t, "timesteps", F32)
+    out = torch.empty((batch, dim), device=t.device, dtype=F32)
+    check(lib().mvd_timestep_embedding_f32(_p(t), t.numel(), _p(out), batch, dim, _stream()),
+          "mvd_timestep_embedding_f32")
+    return out
+
+
+def camera_front(src: torch.Tensor, tgt: torch.Tensor, pos_enc_dim: int, max_freq: float):
+    _contig(src, "source_camera", F32)
+    _contig(tgt, "target_camera", F32)
+    V = src.shape[0]
+    r = torch.empty((V, 9), device=src.device, dtype=F32)
+    enc = torch.empty((V, 6 * pos_enc_dim), device=src.device, dtype=F32)
+    check(lib().mvd_camera_front_f32(_p(src), _p(tgt), _p(r), _p(enc), V, pos_enc_dim, float(max_freq), _stream()),
+          "mvd_camera_front_f32")
+    return r, enc
+
+
+def conv_in(latents: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n_img: int, mod: Optional[torch.Tensor] = None,
+            strength: float = 1.0) -> torch.Tensor:
+    """latents: fp32 NCHW [n_lat,4,H,W]; w: bf16 [Cout,3,3,4]; returns NHWC bf16 [n_img,H,W,Cout]."""
+    _contig(latents, "latents", F32)
+    _contig(w, "w")
+    n_lat, c, H, W = latents.shape
+    if c != 4:
+        raise ValueError("conv_in expects 4 latent channels")
+    cout = w.shape[0]
+    V = 0
+    if mod is not None:
+        _contig(mod, "mod", F32)
+        V = mod.shape[0]
+        if mod.shape[1] != 8 or n_img % V != 0:
+            raise ValueError("mod must be [V, 8] with n_img a multiple of V")
+    out = torch.empty((n_img, H, W, cout), device=latents.device, dtype=BF16)
+    check(lib().mvd_conv_in_f32_bf16(_p(latents), n_lat, _p(mod), V, float(strength), _p(w), _p(bias), _p(out), n_img,
+                                     H, W, cout, _stream()), "mvd_conv_in_f32_bf16")
+    return out
+
+
+def conv_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """x: NHWC bf16 [N,H,W,Cin]; w: bf16 [4,3,3,Cin]; returns fp32 NCHW [N,4,H,W]."""
+    _contig(x, "x")
+    _contig(w, "w")
+    n, H, W, cin = x.shape
+    out = torch.empty((n, 4, H, W), device=x.device, dtype=F32)
+    check(lib().mvd_conv_out_bf16_f32(_p(x), _p(w), _p(bias), _p(out), n, H, W, cin, _stream()),
+          "mvd_conv_out_bf16_f32")
+    return out
+
+
+def upsample2x(x: torch.Tensor) -> torch.Tensor:
+    _contig(x, "x")
+    n, H, W, C = x.shape
+    out = torch.empty((n, 2 * H, 2 * W, C), device=x.device, dtype=BF16)
+    check(lib().mvd_upsample_nearest2x_bf16(_p(x), _p(out), n, H, W, C, _stream()), "mvd_upsample_nearest2x_bf16")
+    return out
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _contig(a, "a")
+    _contig(b, "b")
+    if a.shape != b.shape:
+        raise ValueError("shape mismatch")
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().mvd_add_bf16(_p(a), _p(b), _p(out), a.numel(), _stream()), "mvd_add_bf16")
+    return out
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _contig(x, "x", F32)
+    out = torch.empty(x.shape, device=x.device, dtype=BF16)
+    check(lib().mvd_cast_f32_bf16(_p(x), _p(out), x.numel(), _stream()), "mvd_cast_f32_bf16")
+    return out
+
+
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def transpose_batched(x: torch.Tensor, out_dtype=BF16) -> torch.Tensor:
+    """x: contiguous [B, R, C] (fp32 or bf16) -> [B, C, R] of out_dtype. NCHW<->NHWC with R/C = channels/pixels."""
+    if x.dtype not in _DT or out_dtype not in _DT:
+        raise ValueError("transpose supports fp32 and bf16")
+    _contig(x, "x", x.dtype)
+    B, R, C = x.shape
+    out = torch.empty((B, C, R), device=x.device, dtype=out_dtype)
+    check(lib().mvd_transpose_batched(_p(x), _p(out), B, R, C, _DT[x.dtype], _DT[out_dtype], _stream()),
+          "mvd_transpose_batched")
+    return out
+
+
+def cfg_ddpm_step(model_out: torch.Tensor, latents: torch.Tensor, noise: Optional[torch.Tensor], cfg: int,
+                  guidance: float, sqrt_abar: float, sqrt_1m_abar: float, c_x0: float, c_xt: float,
+                  sigma: float) -> torch.Tensor:
+    """In-place DDPM step on fp32 latents; model_out fp32 [cfg * latents.numel()]."""
+    _contig(model_out, "model_out", F32)
+    _contig(latents, "latents", F32)
+    n = latents.numel()
+    if model_out.numel() != cfg * n:
+        raise ValueError("model_out must hold cfg * latents elements")
+    if noise is not None:
+        _contig(noise, "noise", F32)
+    check(lib().mvd_cfg_ddpm_step_f32(_p(model_out), _p(latents), _p(noise), n, cfg, float(guidance), float(sqrt_abar),
+                                      float(sqrt_1m_abar), float(c_x0), float(c_xt), float(sigma), _stream()),
+          "mvd_cfg_ddpm_step_f32")
+    return latents
