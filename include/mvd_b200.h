@@ -47,15 +47,15 @@ int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t 
                     int geglu, int tile_n, void* stream);
 
 /* 3x3 convolution, padding 1, stride 1 or 2, NHWC bf16, implicit GEMM.
- * out[n, y, x, :] = sum_taps [x | x2](n, s*y+ky-1, s*x+kx-1, :) @ w[:, ky, kx, :]^T + bias + img_bias[n, :]
+ * out[n, y, x, :] = sum_taps [x | x2](n, s*y+ky-1, s*x+kx-1, :) @ w[:, ky, kx, :]^T + bias + img_bias[n, :] (fp32, row stride img_bias_ld)
  *                   (+ residual[n, y, x, :]).
  * Replaces diffusers ResnetBlock2D.conv1/conv2, Downsample2D.conv (stride 2), Upsample2D.conv
  * (invoked from src/models/mvd_unet.py:318 and src/models/image_encoder.py:105).
  * x2 (optional) is a second channel block concatenated after x (skip connections of the up path).
  * cin1, cin2 multiples of 64; c_out multiple of 32; h_out/w_out are OUTPUT sizes. */
 int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
-                     const float* img_bias, const void* residual, void* out, int n_img, int h_out, int w_out,
-                     int c_out, int stride, int tile_n, void* stream);
+                     const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
+                     int w_out, int c_out, int stride, int tile_n, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused flash-attention forward, head_dim 64 (tcgen05 + TMEM + TMA), csrc/attn.cu
@@ -120,9 +120,10 @@ int mvd_small_linear_f32(const float* x, int64_t ldx, const void* w, const void*
 int mvd_timestep_embedding_f32(const float* timesteps, int n_timesteps, float* out, int batch, int dim, void* stream);
 
 /* CameraEncoder.compute_relative_transform + the sinusoidal part of positional_encoding
- * (src/models/camera_encoder.py:107-120,137-151). cams fp32 [V,3,4]; r_flat [V,9]; t_enc [V, 6*pos_enc_dim]. */
-int mvd_camera_front_f32(const float* source_cam, const float* target_cam, float* r_flat, float* t_enc, int n_views,
-                         int pos_enc_dim, float max_freq, void* stream);
+ * (src/models/camera_encoder.py:107-120,137-151). cams fp32 [V,3,4]; r_flat [V,9]; t_enc [V, 6*pos_enc_dim];
+ * t_rel [V,3] (optional, may be NULL). */
+int mvd_camera_front_f32(const float* source_cam, const float* target_cam, float* r_flat, float* t_enc, float* t_rel,
+                         int n_views, int pos_enc_dim, float max_freq, void* stream);
 
 /* UNet conv_in (Conv2d(4,Cout,3,p=1)) on fp32 NCHW latents -> NHWC bf16, with the input-latent FiLM of
  * src/models/mvd_unet.py:256-258 (mod fp32 [n_cam, 8] or NULL) and the CFG duplication of

@@ -49,7 +49,7 @@ _SIGNATURES = {
     "mvd_last_error": (c_char_p, []),
     "mvd_abi_version": (_I, []),
     "mvd_linear_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
-    "mvd_conv3x3_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mvd_conv3x3_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mvd_attention_bf16": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P]),
     "mvd_groupnorm_workspace_floats": (_L, [_I, _I, _I]),
     "mvd_groupnorm_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _F, _I, _P, _L, _P]),
@@ -60,7 +60,7 @@ _SIGNATURES = {
     "mvd_film_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "mvd_small_linear_f32": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "mvd_timestep_embedding_f32": (_I, [_P, _I, _P, _I, _I, _P]),
-    "mvd_camera_front_f32": (_I, [_P, _P, _P, _P, _I, _I, _F, _P]),
+    "mvd_camera_front_f32": (_I, [_P, _P, _P, _P, _P, _I, _I, _F, _P]),
     "mvd_conv_in_f32_bf16": (_I, [_P, _I, _P, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mvd_conv_out_bf16_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mvd_upsample_nearest2x_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P]),

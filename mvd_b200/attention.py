@@ -1,0 +1,211 @@
+"""Drop-in for the reference's `src/models/attention.py`: same class / factory names, same parameters
+(state-dict keys), same attention-processor protocol — the arithmetic runs in libmvd_b200.so.
+
+    out = original_processor(h) + ref_scale * to_out_ref(SDPA(to_q_ref(h), to_k_ref(r), to_v_ref(r)))
+    r   = normalise(ref_hidden_states[name])            (reference attention.py:95-103)
+
+B200 mapping of one processor call (reference attention.py:48-188):
+  1. ONE tcgen05 GEMM projects h to [q | k | v | q_ref] (self) or [q | q_ref] (text cross-attention).
+  2. K/V of the normalised reference features are STEP-INVARIANT (the reference features come from a frozen
+     UNet at t = 0): refnorm + one GEMM, cached per reference tensor. K/V of the text likewise.
+  3. Two flash-attention launches read their heads in place and write O_orig | O_ref side by side.
+  4. ONE GEMM with K = 2C applies [W_out | ref_scale * W_out_ref], adds both biases and the transformer
+     block's residual in its epilogue.
+`S_kv` of the reference branch is arbitrary: a 3-D `[B, S_kv, C]` reference (e.g. all N views' tokens
+concatenated, plus any injected rows) goes through the same kernels (north-star "cross-view" mode).
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .unet import BF16, AttnProcessor2_0, _bf16, _versions, nhwc_view
+
+
+def log_debug(file_path, message):  # reference src/utils.py:25-34; callers here never build tensor f-strings
+    return None
+
+
+class ImageCrossAttentionProcessor(nn.Module):
+    def __init__(self, name: str, query_dim: int, heads: int, dim_head: int = 64, dropout: float = 0.0,
+                 img_ref_scale: float = 0.3):
+        super().__init__()
+        self.name = name
+        self.heads = heads
+        self.dim_head = dim_head
+        self.inner_dim = heads * dim_head
+        self.query_dim = query_dim
+        self.original_processor = None
+        self.to_q_ref = nn.Linear(query_dim, self.inner_dim, bias=False)
+        self.to_k_ref = nn.Linear(query_dim, self.inner_dim, bias=False)
+        self.to_v_ref = nn.Linear(query_dim, self.inner_dim, bias=False)
+        self.ref_ln = nn.LayerNorm(self.inner_dim)  # registered, trainable, unused — as in the reference (:37,160)
+        self.feature_adapter = None
+        self.to_out_ref = nn.ModuleList([nn.Linear(self.inner_dim, query_dim, bias=True), nn.Dropout(dropout)])
+        self.ref_scale_val = img_ref_scale
+
+    # ---- packed weights -----------------------------------------------------------------------------------
+    def _pack(self, attn):
+        own = [self.to_q_ref.weight, self.to_k_ref.weight, self.to_v_ref.weight, self.to_out_ref[0].weight,
+               self.to_out_ref[0].bias]
+        theirs = [attn.to_q.weight, attn.to_k.weight, attn.to_v.weight, attn.to_out[0].weight, attn.to_out[0].bias]
+        key = (_versions(*own, *theirs), float(self.ref_scale_val))
+        cached = self.__dict__.get("_pack_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        s = float(self.ref_scale_val)
+        with torch.no_grad():
+            fused_native = isinstance(self.original_processor, AttnProcessor2_0)
+            p: Dict[str, Any] = dict(fused=fused_native)
+            p["wkv_ref"] = _bf16(torch.cat([self.to_k_ref.weight, self.to_v_ref.weight], 0))
+            if fused_native:
+                is_cross = attn.to_k.weight.shape[1] != attn.to_q.weight.shape[1] or getattr(attn, "is_cross", False)
+                p["is_cross"] = is_cross
+                if is_cross:
+                    p["w_in"] = _bf16(torch.cat([attn.to_q.weight, self.to_q_ref.weight], 0))  # [q | q_ref]
+                else:
+                    p["w_in"] = _bf16(torch.cat([attn.to_q.weight, attn.to_k.weight, attn.to_v.weight,
+                                                 self.to_q_ref.weight], 0))  # [q | k | v | q_ref]
+                p["w_out"] = _bf16(torch.cat([attn.to_out[0].weight.float(), s * self.to_out_ref[0].weight.float()], 1))
+                p["b_out"] = _bf16(attn.to_out[0].bias.float() + s * self.to_out_ref[0].bias.float())
+            else:
+                p["wq_ref"] = _bf16(self.to_q_ref.weight)
+                p["w_out"] = _bf16(s * self.to_out_ref[0].weight.float())
+                p["b_out"] = _bf16(s * self.to_out_ref[0].bias.float())
+        self.__dict__["_pack_cache"] = (key, p)
+        self.__dict__["_ref_cache"] = None
+        return p
+
+    # ---- step-invariant reference K/V ---------------------------------------------------------------------
+    def _reference_kv(self, ref: torch.Tensor, pk) -> torch.Tensor:
+        """[B_ref * S_kv, 2C] = [to_k_ref(r) | to_v_ref(r)], r = normalised reference (attention.py:95-132)."""
+        key = (ref.data_ptr(), ref._version, tuple(ref.shape), tuple(ref.stride()), ref.dtype)
+        cached = self.__dict__.get("_ref_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        if not ref.is_cuda:
+            raise ValueError("reference features must be CUDA tensors")
+        if ref.dim() == 4:  # [B,C,H,W]: statistics per pixel over (batch, channel); tokens = NHWC rows
+            tok = nhwc_view(ref if ref.dtype in (BF16, torch.float32) else ref.float())
+            b, hh, ww, c = tok.shape
+            tok = tok.reshape(b, hh * ww, c)
+            per_pixel = True
+        elif ref.dim() == 3:  # [B,S,C]: statistics per channel over (batch, sequence)
+            tok = ref
+            if tok.dtype != BF16:
+                tok = ops.cast_bf16(tok.float().contiguous())
+            tok = tok.contiguous()
+            per_pixel = False
+        else:
+            raise ValueError(f"reference features must be 3-D or 4-D, got {ref.dim()}-D")
+        if tok.shape[-1] != self.query_dim:
+            raise ValueError(f"{self.name}: reference has {tok.shape[-1]} channels, expected {self.query_dim}")
+        normed = ops.refnorm(tok.contiguous(), per_pixel=per_pixel)
+        b, s, c = normed.shape
+        kv = ops.linear(normed.view(b * s, c), pk["wkv_ref"])
+        self.__dict__["_ref_cache"] = (key, kv, ref)  # hold `ref` so its storage cannot be recycled under the key
+        return kv
+
+    # ---- the processor protocol ---------------------------------------------------------------------------
+    def __call__(self, attn: Any, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None,
+                 ref_hidden_states: Optional[Dict[str, torch.Tensor]] = None,
+                 residual: Optional[torch.Tensor] = None, *args, **kwargs) -> torch.Tensor:
+        kwargs.pop("debug_log_file_path", None)
+        native = isinstance(self.original_processor, AttnProcessor2_0)
+        if ref_hidden_states is None or self.name not in ref_hidden_states:
+            # reference attention.py:72-81: silently fall through to the original processor
+            if native:
+                return self.original_processor(attn, hidden_states, encoder_hidden_states, attention_mask, temb=temb,
+                                               residual=residual)
+            out = self.original_processor(attn, hidden_states, encoder_hidden_states, attention_mask, temb=temb,
+                                          *args, **kwargs)
+            return out if residual is None else ops.add(out.contiguous(), residual.contiguous())
+        if attention_mask is not None:
+            raise NotImplementedError("attention masks are not on MVD's hot path")
+        if hidden_states.dim() != 3:
+            raise ValueError("hidden_states must be [B, HW, C] (the 4-D branch of the reference is dead code)")
+        if not hidden_states.is_cuda or hidden_states.dtype != BF16:
+            raise ValueError("hidden_states must be a CUDA bf16 tensor (no CPU / fp32 fallback path)")
+        pk = self._pack(attn)
+        b, s, c = hidden_states.shape
+        hs2d = hidden_states.reshape(b * s, c)
+        kv_ref = self._reference_kv(ref_hidden_states[self.name], pk)
+        rows = kv_ref.shape[0]
+        if rows % b:
+            raise ValueError(f"{self.name}: {rows} reference tokens do not split over query batch {b}")
+        # reference attention.py:130,132: key.view(batch_size, -1, heads, dim_head) — a flat re-view by the QUERY
+        # batch (with CFG and an un-repeated reference each sample sees a different half of the tokens)
+        k_ref = kv_ref[:, :c].view(b, rows // b, c)
+        v_ref = kv_ref[:, c:].view(b, rows // b, c)
+        res2d = residual.reshape(b * s, c) if residual is not None else None
+        scale = self.dim_head ** -0.5
+
+        if pk["fused"]:
+            cat = torch.empty((b, s, 2 * c), device=hidden_states.device, dtype=BF16)
+            if pk["is_cross"]:
+                proj = ops.linear(hs2d, pk["w_in"]).view(b, s, 2 * c)
+                q, q_ref = proj[:, :, :c], proj[:, :, c:]
+                kv = attn.context_kv(encoder_hidden_states)
+                k, v = kv[:, :, :c], kv[:, :, c:]
+            else:
+                proj = ops.linear(hs2d, pk["w_in"]).view(b, s, 4 * c)
+                q, k, v, q_ref = (proj[:, :, i * c:(i + 1) * c] for i in range(4))
+            ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])
+            ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:])
+            out = ops.linear(cat.view(b * s, 2 * c), pk["w_out"], bias=pk["b_out"], residual=res2d)
+            return out.view(b, s, c)
+
+        # foreign original processor (e.g. a stock diffusers processor): run it as is, add our branch on top
+        original = self.original_processor(attn, hidden_states, encoder_hidden_states, attention_mask, temb=temb,
+                                           *args, **kwargs)
+        base = original.reshape(b * s, c).contiguous()
+        if res2d is not None:
+            base = ops.add(base, res2d.contiguous())
+        q_ref = ops.linear(hs2d, pk["wq_ref"]).view(b, s, c)
+        o = ops.attention(q_ref, k_ref, v_ref, self.heads, scale)
+        return ops.linear(o.view(b * s, c), pk["w_out"], bias=pk["b_out"], residual=base).view(b, s, c)
+
+    def _adapt_reference_features(self, reference_states, target_dim):
+        """reference attention.py:190-197 (kept for API parity): NCHW -> [B, HW, C] view."""
+        if reference_states.ndim == 4:
+            t = nhwc_view(reference_states)
+            return t.reshape(t.shape[0], -1, t.shape[-1])
+        return reference_states
+
+    def load_original_weights(self, attn_module):
+        """reference attention.py:199-246: q/out copied; k/v copied when shapes agree (self-attention), else a
+        transposed leading slice of the text-attention weights, or zero-padded columns."""
+        with torch.no_grad():
+            self.to_q_ref.weight.copy_(attn_module.to_q.weight)
+            self.to_out_ref[0].weight.copy_(attn_module.to_out[0].weight)
+            self.to_out_ref[0].bias.copy_(attn_module.to_out[0].bias)
+            for dst, src in ((self.to_k_ref.weight, attn_module.to_k.weight),
+                             (self.to_v_ref.weight, attn_module.to_v.weight)):
+                d_out, d_in = dst.shape
+                s_out, s_in = src.shape
+                if (d_out, d_in) == (s_out, s_in):
+                    dst.copy_(src)
+                elif d_in >= s_in:
+                    dst[:, :s_in].copy_(src[: min(d_out, s_out), :])
+                    if d_in > s_in:
+                        dst[:, s_in:].zero_()
+                else:
+                    dst.copy_(src[: min(d_out, s_out), :d_in].t())
+
+
+def get_attention_processor_for_module(name, attn_module, img_ref_scale=0.3):
+    """reference attention.py:248-265."""
+    query_dim = attn_module.to_q.in_features
+    heads = attn_module.heads
+    processor = ImageCrossAttentionProcessor(name=name, query_dim=query_dim, heads=heads,
+                                             dim_head=attn_module.to_q.out_features // heads,
+                                             img_ref_scale=img_ref_scale)
+    processor.original_processor = attn_module.processor
+    w = attn_module.to_q.weight
+    processor.to(device=w.device, dtype=w.dtype)
+    processor.load_original_weights(attn_module)
+    return processor

@@ -1,0 +1,170 @@
+"""Drop-in for the reference's `src/models/camera_encoder.py` (same class, constructor, parameter names and
+public methods); pose embedding and FiLM modulation run in libmvd_b200.so.
+
+  encode_cameras(src, tgt) -> fp32 [V, output_dim]      reference camera_encoder.py:160-196
+  apply_modulation(x | tuple, name, emb)                 reference camera_encoder.py:198-255
+
+Differences that are deliberate and documented (DESIGN.md "reference quirks"):
+  * the reference draws a fresh `torch.randn` projection inside positional_encoding on every call
+    (camera_encoder.py:153-156). Here the matrix is an explicit, injectable input
+    (`set_positional_projection`); when none is injected a fresh one is drawn per call from
+    `self.generator` with the same distribution, i.e. the reference's semantics.
+  * `_current_modulation_stats` stays empty: filling it costs 8 device->host syncs per site
+    (camera_encoder.py:230-253) and nothing on the inference path reads it.
+  * with CFG (batch = 2V) the reference's broadcast raises for V > 1; here sample n uses camera n % V.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .unet import BF16, _bf16, _versions, nhwc_view, nchw_shape, _small_linear_any_m
+
+
+def _mlp(dims, final_norm: bool = False) -> nn.Sequential:
+    layers = []
+    for i in range(len(dims) - 1):
+        layers.append(nn.Linear(dims[i], dims[i + 1]))
+        if i < len(dims) - 2:
+            layers += [nn.LayerNorm(dims[i + 1]), nn.SiLU()]
+    if final_norm:
+        layers.append(nn.LayerNorm(dims[-1]))
+    return nn.Sequential(*layers)
+
+
+def _run_mlp(seq: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """Linear / LayerNorm(+SiLU) chains on fp32 [M<=16.., K] rows through the skinny-linear and LN kernels."""
+    mods = list(seq)
+    i = 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.Linear):
+            x = _small_linear_any_m(x, _bf16(m.weight), _bf16(m.bias))
+            i += 1
+        elif isinstance(m, nn.LayerNorm):
+            fuse = i + 1 < len(mods) and isinstance(mods[i + 1], nn.SiLU)
+            x = ops.layernorm_f32(x.contiguous(), _bf16(m.weight), _bf16(m.bias), m.eps, silu=fuse)
+            i += 2 if fuse else 1
+        else:
+            raise TypeError(f"unexpected layer {type(m).__name__} in camera MLP")
+    return x
+
+
+class CameraEncoder(nn.Module):
+    def __init__(self, output_dim: int = 768, hidden_dim: int = 512, max_freq: int = 10,
+                 modulation_hidden_dims: Dict[str, int] = None, modulation_strength: float = 1.0,
+                 simple_encoder: bool = False):
+        super().__init__()
+        self.output_dim, self.hidden_dim, self.max_freq, self.simple_encoder = output_dim, hidden_dim, max_freq, simple_encoder
+        self.pos_enc_dim = (output_dim // 2) // 3
+        mid = [hidden_dim] if simple_encoder else [hidden_dim, hidden_dim]
+        self.rotation_encoder = _mlp([9] + mid + [output_dim])
+        self.translation_encoder = _mlp([output_dim] + mid + [output_dim])
+        self.final_projection = _mlp([2 * output_dim, output_dim, output_dim], final_norm=True)
+        self.output_norm = nn.LayerNorm(output_dim)
+        self.modulation_hidden_dims = modulation_hidden_dims or {}
+        self.modulators = nn.ModuleDict()
+        for name, dim in self.modulation_hidden_dims.items():
+            self.modulators[name] = _mlp([output_dim, output_dim // 2, dim * 2])
+        self.init_modulators()
+        self.modulation_strength = modulation_strength
+        self._current_modulation_stats = {}
+        self.generator: Optional[torch.Generator] = None
+        self._pos_proj: Optional[torch.Tensor] = None
+
+    def init_modulators(self):
+        """reference camera_encoder.py:92-105."""
+        for modulator in self.modulators.values():
+            last = modulator[-1]
+            nn.init.normal_(last.weight, mean=0.0, std=0.02)
+            dim = last.out_features // 2
+            last.bias.data[:dim].fill_(0.5)
+            last.bias.data[dim:].fill_(0.0)
+
+    # ---- positional projection ----------------------------------------------------------------------------
+    def set_positional_projection(self, weight: Optional[torch.Tensor]):
+        """Pin the [output_dim, 6*pos_enc_dim] matrix the reference re-draws on every call (pass None to go back
+        to per-call draws). Needed for parity tests, CUDA-graph replay and deterministic sampling."""
+        if weight is not None:
+            if tuple(weight.shape) != (self.output_dim, 6 * self.pos_enc_dim):
+                raise ValueError(f"projection must be [{self.output_dim}, {6 * self.pos_enc_dim}]")
+            weight = weight.detach().to(device=self.output_norm.weight.device, dtype=BF16).contiguous()
+        self._pos_proj = weight
+        self.__dict__["_emb_cache"] = None
+
+    def _projection(self, device) -> torch.Tensor:
+        if self._pos_proj is not None:
+            return self._pos_proj
+        n = 6 * self.pos_enc_dim
+        w = torch.randn(self.output_dim, n, device=device, generator=self.generator) / math.sqrt(n)
+        return w.to(BF16)
+
+    # ---- embedding ----------------------------------------------------------------------------------------
+    def compute_relative_transform(self, source_camera: torch.Tensor, target_camera: torch.Tensor):
+        """reference camera_encoder.py:107-120: R = R_t R_s^T, T = T_t - R T_s (fp32)."""
+        r_flat, _, t_rel = self._front(source_camera, target_camera)
+        return {"R": r_flat.view(-1, 3, 3), "T": t_rel}
+
+    def _front(self, source_camera, target_camera):
+        dev = self.output_norm.weight.device
+        src = source_camera.to(device=dev, dtype=torch.float32)[:, :3, :4].contiguous()
+        tgt = target_camera.to(device=dev, dtype=torch.float32)[:, :3, :4].contiguous()
+        return ops.camera_front(src, tgt, self.pos_enc_dim, float(self.max_freq))
+
+    def encode_cameras(self, source_camera: torch.Tensor, target_camera: torch.Tensor) -> torch.Tensor:
+        pinned = self._pos_proj is not None
+        key = None
+        if pinned:  # cameras + weights unchanged and projection pinned -> embedding is step-invariant
+            key = (source_camera.data_ptr(), source_camera._version, target_camera.data_ptr(), target_camera._version,
+                   _versions(*self.parameters()))
+            cached = self.__dict__.get("_emb_cache")
+            if cached is not None and cached[0] == key:
+                return cached[1]
+        r_flat, t_enc, _ = self._front(source_camera, target_camera)
+        rot = _run_mlp(self.rotation_encoder, r_flat)
+        trans_in = _small_linear_any_m(t_enc, self._projection(t_enc.device), None)
+        trans = _run_mlp(self.translation_encoder, trans_in)
+        comb = torch.empty((rot.shape[0], 2 * self.output_dim), device=rot.device, dtype=torch.float32)
+        comb[:, : self.output_dim].copy_(rot)
+        comb[:, self.output_dim:].copy_(trans)
+        emb = _run_mlp(self.final_projection, comb)
+        emb = ops.layernorm_f32(emb, _bf16(self.output_norm.weight), _bf16(self.output_norm.bias), self.output_norm.eps)
+        if pinned:
+            self.__dict__["_emb_cache"] = (key, emb, source_camera, target_camera)
+            self.__dict__["_mod_cache"] = {}
+        return emb
+
+    def forward(self, camera_data: Dict[str, torch.Tensor]) -> torch.Tensor:
+        raise NotImplementedError("call encode_cameras(source_camera, target_camera)")
+
+    # ---- FiLM ---------------------------------------------------------------------------------------------
+    def modulation(self, modulator_name: str, camera_embedding: torch.Tensor) -> torch.Tensor:
+        """fp32 [V, 2*dim] raw modulator output (scale logits | shift)."""
+        cache = self.__dict__.get("_mod_cache")
+        emb_cached = self.__dict__.get("_emb_cache")
+        use_cache = cache is not None and emb_cached is not None and emb_cached[1] is camera_embedding
+        if use_cache and modulator_name in cache:
+            return cache[modulator_name]
+        mod = _run_mlp(self.modulators[modulator_name], camera_embedding.float().contiguous())
+        if use_cache:
+            cache[modulator_name] = mod
+        return mod
+
+    def apply_modulation(self, hidden_states, modulator_name: str, camera_embedding: torch.Tensor):
+        if isinstance(hidden_states, tuple):  # down blocks: only the main output is modulated (:201-205)
+            return (self.apply_modulation_to_tensor(hidden_states[0], modulator_name, camera_embedding),) + \
+                tuple(hidden_states[1:])
+        return self.apply_modulation_to_tensor(hidden_states, modulator_name, camera_embedding)
+
+    def apply_modulation_to_tensor(self, tensor, modulator_name, camera_embedding):
+        if modulator_name not in self.modulators or camera_embedding is None:
+            return tensor  # reference :212-219 (e.g. the mid-block hook's name "mid_0" is not a modulator)
+        mod = self.modulation(modulator_name, camera_embedding)
+        if tensor.dtype != BF16:
+            raise ValueError("FiLM expects bf16 channels-last activations (the input-latent site is fused in conv_in)")
+        x = nhwc_view(tensor)
+        return nchw_shape(ops.film(x, mod, float(self.modulation_strength)))

@@ -149,7 +149,8 @@ __global__ void timestep_embed_kernel(const float* __restrict__ t, int n_t, floa
 // src/tgt: fp32 [V, 3, 4]; r_flat: fp32 [V, 9]; enc: fp32 [V, 3 * 2P].
 // ------------------------------------------------------------------------------------------------
 __global__ void camera_front_kernel(const float* __restrict__ src, const float* __restrict__ tgt,
-                                    float* __restrict__ r_flat, float* __restrict__ enc, int V, int P, float max_freq) {
+                                    float* __restrict__ r_flat, float* __restrict__ enc, float* __restrict__ t_rel, int V, int P,
+                                    float max_freq) {
   const int v = blockIdx.x;
   __shared__ float R[9], T[3];
   const float* s = src + v * 12;
@@ -167,6 +168,7 @@ __global__ void camera_front_kernel(const float* __restrict__ src, const float* 
     float acc = 0.f;
     for (int k = 0; k < 3; ++k) acc += R[i * 3 + k] * s[k * 4 + 3];
     T[i] = t[i * 4 + 3] - acc;
+    if (t_rel != nullptr) t_rel[v * 3 + i] = T[i];
   }
   __syncthreads();
   const float lmax = logf(max_freq);
@@ -403,12 +405,12 @@ int mvd_timestep_embedding_f32(const float* timesteps, int n_timesteps, float* o
   return MVD_OK;
 }
 
-int mvd_camera_front_f32(const float* source_cam, const float* target_cam, float* r_flat, float* t_enc, int n_views,
-                         int pos_enc_dim, float max_freq, void* stream) {
+int mvd_camera_front_f32(const float* source_cam, const float* target_cam, float* r_flat, float* t_enc, float* t_rel,
+                         int n_views, int pos_enc_dim, float max_freq, void* stream) {
   using namespace mvd;
   MVD_CHECK(n_views > 0 && pos_enc_dim > 0, "camera_front: bad shape");
   camera_front_kernel<<<n_views, 128, 0, static_cast<cudaStream_t>(stream)>>>(source_cam, target_cam, r_flat, t_enc,
-                                                                              n_views, pos_enc_dim, max_freq);
+                                                                              t_rel, n_views, pos_enc_dim, max_freq);
   MVD_CUDA(cudaGetLastError());
   return MVD_OK;
 }

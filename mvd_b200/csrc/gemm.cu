@@ -549,16 +549,16 @@ int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t 
 }
 
 int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
-                     const float* img_bias, const void* residual, void* out, int n_img, int h_out, int w_out,
-                     int c_out, int stride, int tile_n, void* stream) {
+                     const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
+                     int w_out, int c_out, int stride, int tile_n, void* stream) {
   using namespace mvd;
   MVD_CHECK(n_img > 0 && h_out > 0 && w_out > 0, "conv3x3: empty problem");
   MVD_CHECK(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
   OperandA s1{x, cin1, cin1};
   OperandA s2{x2, cin2, cin2};
   const int cin = cin1 + ((x2 && cin2 > 0) ? cin2 : 0);
-  return run_gemm_conv(s1, (x2 && cin2 > 0) ? &s2 : nullptr, w, static_cast<int64_t>(9) * cin, bias, img_bias, c_out,
-                       /*rows_per_group=*/0, residual, c_out, out, c_out, n_img, h_out, w_out, c_out, /*ntaps=*/9,
+  return run_gemm_conv(s1, (x2 && cin2 > 0) ? &s2 : nullptr, w, static_cast<int64_t>(9) * cin, bias, img_bias,
+                       img_bias_ld > 0 ? img_bias_ld : c_out, /*rows_per_group=*/0, residual, c_out, out, c_out, n_img, h_out, w_out, c_out, /*ntaps=*/9,
                        stride, /*geglu=*/0, tile_n, static_cast<cudaStream_t>(stream));
 }
 

@@ -1,0 +1,254 @@
+"""Drop-in for the reference's `src/models/mvd_unet.py`: `MultiViewUNet`, `UNetOutput`, `create_mvd_pipeline`
+with the reference's constructor/forward keywords and attributes, orchestrating one denoise step
+(reference mvd_unet.py:179-338) over the sm_100a kernels.
+
+What is kept literally: the 32-processor installation and both name maps (mvd_unet.py:106-162), the FiLM forward
+hooks on every down/mid/up block — including the reference's quirks that only `output[0]` of a down block is
+modulated and that the mid hook is registered under the name "mid_0", which is not a modulator and therefore a
+no-op (mvd_unet.py:357-376, camera_encoder.py:212-213) — the "output" modulator applied to the INPUT latents
+(mvd_unet.py:256-258, fused into conv_in here), the text-embedding selection for the image encoder under CFG
+(mvd_unet.py:278-285) and `UNetOutput`.
+
+What is different by design: no `log_debug` tensor statistics (each cost a device->host sync in the reference,
+src/utils.py:25-34), step-invariant work (reference-UNet features, reference/text K/V, camera embedding when the
+positional projection is pinned) is cached, and `matched_batch_cfg=True` repeats per-view conditioning over the
+CFG halves instead of the reference's flat re-view.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .attention import get_attention_processor_for_module
+from .camera_encoder import CameraEncoder
+from .image_encoder import ImageEncoder
+from .scheduler import DDPMScheduler, ShiftSNRScheduler
+from .unet import BF16, UNet2DConditionModel, _small_linear_any_m, nhwc_view, nchw_shape
+
+
+class UNetOutput(NamedTuple):
+    sample: torch.Tensor
+
+
+def _resolve_unet_config(pretrained_model_name_or_path) -> dict:
+    """No network and no diffusers here: the UNet is built from the SD2.1 architecture (random init) and weights
+    are loaded afterwards with load_state_dict (keys match diffusers'). A dict overrides config entries."""
+    if isinstance(pretrained_model_name_or_path, dict):
+        return dict(pretrained_model_name_or_path)
+    return {}
+
+
+class MultiViewUNet(nn.Module):
+    def __init__(self, pretrained_model_name_or_path=None, dtype: torch.dtype = torch.float32,
+                 use_memory_efficient_attention: bool = True, enable_gradient_checkpointing: bool = True,
+                 img_ref_scale: float = 0.3, cam_modulation_strength: float = 0.2, cam_output_dim: int = 1024,
+                 cam_hidden_dim: int = 512, use_camera_conditioning: bool = True, use_image_conditioning: bool = True,
+                 simple_cam_encoder: bool = False, matched_batch_cfg: bool = False):
+        super().__init__()
+        self.use_camera_conditioning = use_camera_conditioning
+        self.use_image_conditioning = use_image_conditioning
+        self.cam_output_dim, self.cam_hidden_dim, self.simple_cam_encoder = cam_output_dim, cam_hidden_dim, simple_cam_encoder
+        self.matched_batch_cfg = matched_batch_cfg
+        cfg = _resolve_unet_config(pretrained_model_name_or_path)
+        self.base_unet = UNet2DConditionModel(**cfg)
+        self.config = self.base_unet.config
+        self.device = torch.device("cpu")
+        self.dtype = dtype
+        self.img_ref_scale = img_ref_scale
+
+        down_channels = list(self.config.block_out_channels)
+        up_channels = list(reversed(down_channels))
+        dims = {f"down_{i}": down_channels[min(i, len(down_channels) - 1)] for i in range(len(self.base_unet.down_blocks))}
+        dims.update({f"up_{i}": up_channels[i] for i in range(len(self.base_unet.up_blocks))})
+        dims["mid"] = down_channels[-1]
+        dims["output"] = 4
+        self.camera_encoder = CameraEncoder(output_dim=cam_output_dim, hidden_dim=cam_hidden_dim,
+                                            modulation_hidden_dims=dims, modulation_strength=cam_modulation_strength,
+                                            simple_encoder=simple_cam_encoder) if use_camera_conditioning else None
+        self.image_encoder = ImageEncoder(pretrained_model_name_or_path, dtype=dtype,
+                                          expected_sample_size=self.config.sample_size,
+                                          unet_config=cfg) if use_image_conditioning else None
+        self.hooks = []
+        self.current_camera_embedding = None
+        self._init_image_cross_attention()
+        super().to(dtype=dtype)
+
+    # ---- reference mvd_unet.py:106-162 ------------------------------------------------------------------------
+    def _init_image_cross_attention(self):
+        self.attention_layer_map = {}
+        self.feature_to_attention_map = {}
+
+        def install(prefix, attentions):
+            for j, attn_block in enumerate(attentions):
+                for tb in attn_block.transformer_blocks:
+                    feature = f"{prefix}_attn_{j}"
+                    names = []
+                    for suffix, module in (("self", tb.attn1), ("cross", tb.attn2)):
+                        name = f"{feature}_{suffix}"
+                        self._replace_attention_processor(module, name)
+                        names.append(name)
+                    self.feature_to_attention_map[feature] = names
+
+        for i, block in enumerate(self.base_unet.down_blocks):
+            if hasattr(block, "attentions"):
+                install(f"down_block_{i}", block.attentions)
+        if hasattr(self.base_unet.mid_block, "attentions"):
+            install("mid_block", self.base_unet.mid_block.attentions)
+        for i, block in enumerate(self.base_unet.up_blocks):
+            if hasattr(block, "attentions"):
+                install(f"up_block_{i}", block.attentions)
+
+    def _replace_attention_processor(self, attn_module, name):
+        processor = get_attention_processor_for_module(name, attn_module, img_ref_scale=self.img_ref_scale)
+        self.attention_layer_map[name] = attn_module
+        attn_module.processor = processor
+
+    def to(self, *args, **kwargs):
+        device = args[0] if args and not isinstance(args[0], torch.dtype) else kwargs.get("device", self.device)
+        self.device = torch.device(device) if device is not None else self.device
+        if "dtype" in kwargs and kwargs["dtype"] is not None:
+            self.dtype = kwargs["dtype"]
+        if self.image_encoder is not None:
+            self.image_encoder.device = self.device
+        return super().to(*args, **kwargs)
+
+    # ---- reference mvd_unet.py:179-338 ------------------------------------------------------------------------
+    def forward(self, sample: torch.Tensor, timestep, encoder_hidden_states: torch.Tensor,
+                source_camera: Optional[torch.Tensor] = None, target_camera: Optional[torch.Tensor] = None,
+                source_image_latents: Optional[torch.Tensor] = None, return_dict: bool = True,
+                timestep_cond=None, cross_attention_kwargs: Optional[Dict[str, Any]] = None, added_cond_kwargs=None):
+        if cross_attention_kwargs and "debug_log_file_path" in cross_attention_kwargs:
+            cross_attention_kwargs = {k: v for k, v in cross_attention_kwargs.items() if k != "debug_log_file_path"}
+        dev = self.base_unet.device
+        if dev.type != "cuda":
+            raise RuntimeError("MultiViewUNet runs on a CUDA device only (no CPU path); call .to('cuda') first")
+        sample = sample.to(device=dev)
+        text = self._prepare_text(encoder_hidden_states.to(device=dev), sample.shape[0])
+
+        self.current_camera_embedding = None
+        self.base_unet.input_film = None
+        if self.use_camera_conditioning and target_camera is not None:
+            self._manage_modulation_hooks(register=True)
+            self.current_camera_embedding = self.camera_encoder.encode_cameras(source_camera, target_camera)
+            # "output" modulator on the input latents (mvd_unet.py:256-258): fused into conv_in
+            mod = self.camera_encoder.modulation("output", self.current_camera_embedding)
+            self.base_unet.input_film = (mod, float(self.camera_encoder.modulation_strength))
+
+        ref_hidden_states = None
+        if self.use_image_conditioning and source_image_latents is not None:
+            batch_size = source_image_latents.shape[0]
+            ie_text = text
+            if text.shape[0] == 2 * batch_size:  # CFG: the conditional half (mvd_unet.py:280-283)
+                ie_text = text[batch_size:]
+            elif text.shape[0] > batch_size:
+                ie_text = text[:batch_size]
+            features = self.image_encoder(latents=source_image_latents.to(device=dev), text_embeddings=ie_text,
+                                          timestep=0)
+            if self.matched_batch_cfg and sample.shape[0] > batch_size:
+                features = self._repeat_features(features, sample.shape[0] // batch_size)
+            ref_hidden_states = self._map_image_features_to_attention_layers(features)
+
+        kw = dict(cross_attention_kwargs or {})
+        if ref_hidden_states is not None:
+            kw["ref_hidden_states"] = ref_hidden_states
+        output = self.base_unet(sample=sample, timestep=timestep, encoder_hidden_states=text, return_dict=True,
+                                timestep_cond=timestep_cond, cross_attention_kwargs=kw,
+                                added_cond_kwargs=added_cond_kwargs)
+        hidden_states = output.sample
+        if not return_dict:
+            return hidden_states
+        return UNetOutput(sample=hidden_states)
+
+    # ---- helpers ----------------------------------------------------------------------------------------------
+    def _prepare_text(self, text: torch.Tensor, batch: int) -> torch.Tensor:
+        """bf16 cast + CFG repeat (mvd_unet.py:233-237), cached per text tensor (constant across steps)."""
+        key = (text.data_ptr(), text._version, tuple(text.shape), text.dtype, batch)
+        cached = self.__dict__.get("_text_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        t = text
+        if t.dtype != BF16:
+            t = ops.cast_bf16(t.float().contiguous())
+        if batch > t.shape[0]:
+            t = t.repeat(batch // t.shape[0], 1, 1)
+        t = t.contiguous()
+        self.__dict__["_text_cache"] = (key, t, text)
+        return t
+
+    def _repeat_features(self, features, times: int):
+        key = (id(features), times)
+        cached = self.__dict__.get("_rep_cache")
+        if cached is not None and cached[0] == key and cached[2] is features:
+            return cached[1]
+        rep = {}
+        for name, f in features.items():
+            v = nhwc_view(f)
+            rep[name] = nchw_shape(v.repeat(times, 1, 1, 1))
+        self.__dict__["_rep_cache"] = (key, rep, features)
+        return rep
+
+    def _map_image_features_to_attention_layers(self, image_features):
+        ref_hidden_states = {}
+        for name, feature in image_features.items():
+            if isinstance(feature, tuple):
+                feature = feature[0]
+            for attn_name in self.feature_to_attention_map.get(name, []):
+                if attn_name in self.attention_layer_map:
+                    ref_hidden_states[attn_name] = feature
+        return ref_hidden_states
+
+    def _manage_modulation_hooks(self, register: bool):
+        """reference mvd_unet.py:354-385 (hooks are registered once and stay)."""
+        if register and not self.hooks:
+            def get_hook(idx, direction):
+                def hook(module, inputs, output):
+                    if self.current_camera_embedding is not None:
+                        return self.camera_encoder.apply_modulation(output, f"{direction}_{idx}",
+                                                                    self.current_camera_embedding)
+                    return output
+                return hook
+
+            targets = [(b, get_hook(i, "down")) for i, b in enumerate(self.base_unet.down_blocks)]
+            targets.append((self.base_unet.mid_block, get_hook(0, "mid")))  # -> "mid_0": not a modulator, no-op
+            targets += [(b, get_hook(i, "up")) for i, b in enumerate(self.base_unet.up_blocks)]
+            for module, fn in targets:
+                self.hooks.append(module.register_forward_hook(fn))
+        elif not register and self.hooks:
+            for h in self.hooks:
+                h.remove()
+            self.hooks = []
+
+
+def create_mvd_pipeline(pretrained_model_name_or_path=None, dtype: torch.dtype = torch.bfloat16,
+                        use_memory_efficient_attention: bool = True, enable_gradient_checkpointing: bool = True,
+                        use_camera_conditioning: bool = True, use_image_conditioning: bool = True,
+                        img_ref_scale: float = 0.25, cam_modulation_strength: float = 1.0, cam_output_dim: int = 1024,
+                        cam_hidden_dim: int = 512, simple_cam_encoder: bool = False, cache_dir=None,
+                        scheduler_config: Optional[Dict[str, Any]] = None, matched_batch_cfg: bool = False,
+                        device: Optional[str] = None):
+    """reference mvd_unet.py:388-453: DDPM scheduler rebuilt on SNR-shifted (interpolated, scale 6) betas + the
+    multi-view UNet. Text encoder and VAE are outside this library's scope (pass prompt_embeds / latents)."""
+    from .pipeline import MVDPipeline
+
+    if device is None:
+        if not torch.cuda.is_available():
+            raise RuntimeError("mvd_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        device = "cuda"
+    scheduler = ShiftSNRScheduler.from_scheduler(noise_scheduler=DDPMScheduler(), shift_mode="interpolated",
+                                                 shift_scale=6.0, scheduler_class=DDPMScheduler)
+    mv_unet = MultiViewUNet(pretrained_model_name_or_path, dtype=dtype,
+                            use_memory_efficient_attention=use_memory_efficient_attention,
+                            enable_gradient_checkpointing=enable_gradient_checkpointing, img_ref_scale=img_ref_scale,
+                            cam_modulation_strength=cam_modulation_strength, cam_output_dim=cam_output_dim,
+                            cam_hidden_dim=cam_hidden_dim, simple_cam_encoder=simple_cam_encoder,
+                            use_camera_conditioning=use_camera_conditioning,
+                            use_image_conditioning=use_image_conditioning, matched_batch_cfg=matched_batch_cfg)
+    mv_unet = mv_unet.to(device=device, dtype=dtype)
+    pipeline = MVDPipeline(unet=mv_unet, scheduler=scheduler)
+    pipeline.use_camera_conditioning = use_camera_conditioning
+    pipeline.use_image_conditioning = use_image_conditioning
+    pipeline.img_ref_scale = img_ref_scale
+    return pipeline

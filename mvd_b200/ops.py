@@ -136,10 +136,11 @@ def conv3x3(
         _req(bias, "bias")
     if img_bias is not None:
         _req(img_bias, "img_bias", torch.float32)
-        if tuple(img_bias.shape) != (n, cout) or not img_bias.is_contiguous():
-            raise ValueError("img_bias must be contiguous fp32 [N, Cout]")
+        if tuple(img_bias.shape) != (n, cout) or img_bias.stride(1) != 1:
+            raise ValueError("img_bias must be fp32 [N, Cout] with unit inner stride")
     check(
-        lib().mvd_conv3x3_bf16(_p(x), c1, _p(x2), c2, _p(w), _p(bias), _p(img_bias), _p(residual), _p(out), n, ho, wo,
+        lib().mvd_conv3x3_bf16(_p(x), c1, _p(x2), c2, _p(w), _p(bias), _p(img_bias),
+                               0 if img_bias is None else img_bias.stride(0), _p(residual), _p(out), n, ho, wo,
                                cout, stride, tile_n, _stream()),
         "mvd_conv3x3_bf16",
     )
@@ -312,9 +313,10 @@ def camera_front(src: torch.Tensor, tgt: torch.Tensor, pos_enc_dim: int, max_fre
     V = src.shape[0]
     r = torch.empty((V, 9), device=src.device, dtype=F32)
     enc = torch.empty((V, 6 * pos_enc_dim), device=src.device, dtype=F32)
-    check(lib().mvd_camera_front_f32(_p(src), _p(tgt), _p(r), _p(enc), V, pos_enc_dim, float(max_freq), _stream()),
-          "mvd_camera_front_f32")
-    return r, enc
+    t_rel = torch.empty((V, 3), device=src.device, dtype=F32)
+    check(lib().mvd_camera_front_f32(_p(src), _p(tgt), _p(r), _p(enc), _p(t_rel), V, pos_enc_dim, float(max_freq),
+                                     _stream()), "mvd_camera_front_f32")
+    return r, enc, t_rel
 
 
 def conv_in(latents: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, n_img: int, mod: Optional[torch.Tensor] = None,

@@ -203,9 +203,9 @@ class Upsample2D(nn.Module):
 class DownBlock(nn.Module):
     """CrossAttnDownBlock2D (has_attn) / DownBlock2D."""
 
-    def __init__(self, cin, cout, heads, cross_dim, has_attn, add_down):
+    def __init__(self, cin, cout, heads, cross_dim, has_attn, add_down, temb_dim=1280):
         super().__init__()
-        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout) for i in range(2)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(cin if i == 0 else cout, cout, temb_dim) for i in range(2)])
         if has_attn:
             self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, cross_dim) for _ in range(2)])
         self.downsamplers = nn.ModuleList([Downsample2D(cout)]) if add_down else None
@@ -227,10 +227,10 @@ class DownBlock(nn.Module):
 class MidBlock(nn.Module):
     """UNetMidBlock2DCrossAttn."""
 
-    def __init__(self, c, heads, cross_dim):
+    def __init__(self, c, heads, cross_dim, temb_dim=1280):
         super().__init__()
         self.attentions = nn.ModuleList([Transformer2DModel(c, heads, cross_dim)])
-        self.resnets = nn.ModuleList([ResnetBlock2D(c, c), ResnetBlock2D(c, c)])
+        self.resnets = nn.ModuleList([ResnetBlock2D(c, c, temb_dim), ResnetBlock2D(c, c, temb_dim)])
 
     def forward(self, h, temb, encoder_hidden_states=None, cross_attention_kwargs=None):
         h = self.resnets[0](h, temb)
@@ -241,13 +241,13 @@ class MidBlock(nn.Module):
 class UpBlock(nn.Module):
     """CrossAttnUpBlock2D (has_attn) / UpBlock2D."""
 
-    def __init__(self, cin, cout, prev_out, heads, cross_dim, has_attn, add_up):
+    def __init__(self, cin, cout, prev_out, heads, cross_dim, has_attn, add_up, temb_dim=1280):
         super().__init__()
         res = []
         for i in range(3):
             skip = cin if i == 2 else cout
             inp = prev_out if i == 0 else cout
-            res.append(ResnetBlock2D(inp + skip, cout))
+            res.append(ResnetBlock2D(inp + skip, cout, temb_dim))
         self.resnets = nn.ModuleList(res)
         if has_attn:
             self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, cross_dim) for _ in range(3)])
@@ -288,16 +288,18 @@ class UNet2DConditionModel(nn.Module):
         self.time_embedding = TimestepEmbedding(ch[0], temb_dim)
         downs, out = [], ch[0]
         for i, c in enumerate(ch):
-            downs.append(DownBlock(out, c, heads[i], cross, cfg["down_has_attn"][i], add_down=i < len(ch) - 1))
+            downs.append(DownBlock(out, c, heads[i], cross, cfg["down_has_attn"][i], add_down=i < len(ch) - 1,
+                                   temb_dim=temb_dim))
             out = c
         self.down_blocks = nn.ModuleList(downs)
-        self.mid_block = MidBlock(ch[-1], heads[-1], cross)
+        self.mid_block = MidBlock(ch[-1], heads[-1], cross, temb_dim)
         rev, rheads = list(reversed(ch)), list(reversed(heads))
         ups, out = [], rev[0]
         for i, c in enumerate(rev):
             prev_out, out = out, c
             cin = rev[min(i + 1, len(ch) - 1)]
-            ups.append(UpBlock(cin, c, prev_out, rheads[i], cross, cfg["up_has_attn"][i], add_up=i < len(ch) - 1))
+            ups.append(UpBlock(cin, c, prev_out, rheads[i], cross, cfg["up_has_attn"][i], add_up=i < len(ch) - 1,
+                               temb_dim=temb_dim))
         self.up_blocks = nn.ModuleList(ups)
         self.conv_norm_out = nn.GroupNorm(cfg["norm_num_groups"], ch[0], eps=cfg["norm_eps"])
         self.conv_act = nn.SiLU()

@@ -142,13 +142,14 @@ def test_camera_front():
     g = torch.Generator().manual_seed(0)
     src = torch.randn(4, 3, 4, generator=g).cuda()
     tgt = torch.randn(4, 3, 4, generator=g).cuda()
-    r, enc = ops.camera_front(src, tgt, 170, 10.0)
+    r, enc, t_rel = ops.camera_front(src, tgt, 170, 10.0)
     R = torch.bmm(tgt[:, :, :3], src[:, :, :3].transpose(1, 2))
     T = tgt[:, :, 3] - torch.bmm(R, src[:, :, 3:]).squeeze(2)
     freqs = torch.exp(torch.linspace(0.0, math.log(10.0), 170, device="cuda"))
     ang = T[:, :, None] * freqs[None, None]
     ref = torch.cat([torch.sin(ang), torch.cos(ang)], -1).reshape(4, -1)
     _close(r, R.reshape(4, 9), "camera R", atol=1e-5, rtol=1e-5)
+    _close(t_rel, T, "camera T", atol=1e-5, rtol=1e-5)
     _close(enc, ref, "camera posenc", atol=2e-4, rtol=0)
 
 
