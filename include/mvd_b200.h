@@ -30,6 +30,8 @@ extern "C" {
 
 const char* mvd_last_error(void);
 int mvd_abi_version(void);
+/* Number of CUDA kernels this library has launched (or recorded into a stream capture) in this process. */
+int64_t mvd_kernel_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Tensor-core contractions (tcgen05 + TMEM + TMA), csrc/gemm.cu
@@ -151,6 +153,14 @@ int mvd_transpose_batched(const void* x, void* out, int batch, int rows, int col
 int mvd_cfg_ddpm_step_f32(const float* model_out, float* latents, const float* noise, int64_t n, int cfg,
                           float guidance, float sqrt_alpha_bar, float sqrt_one_minus_alpha_bar, float coef_x0,
                           float coef_xt, float sigma, void* stream);
+
+/* Device-table variants for replaying the whole sampling loop as one CUDA graph: the per-step
+ * scalars live in coef_table[steps][8] = {t, sqrt_abar, sqrt_1m_abar, c_x0, c_xt, sigma, 0, 0} and are selected by
+ * the device-side counter *step_idx; noise_table is fp32 [steps][n] or NULL. mvd_advance_step increments the
+ * counter (wrapping at n_steps) and writes the next timestep for mvd_timestep_embedding_f32. */
+int mvd_cfg_ddpm_step_table_f32(const float* model_out, float* latents, const float* noise_table, int64_t n, int cfg,
+                                float guidance, const float* coef_table, const int* step_idx, void* stream);
+int mvd_advance_step(int* step_idx, const float* coef_table, float* timestep_out, int n_steps, void* stream);
 
 #ifdef __cplusplus
 }

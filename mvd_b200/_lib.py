@@ -48,6 +48,7 @@ _F = c_float
 _SIGNATURES = {
     "mvd_last_error": (c_char_p, []),
     "mvd_abi_version": (_I, []),
+    "mvd_kernel_launch_count": (_L, []),
     "mvd_linear_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "mvd_conv3x3_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mvd_attention_bf16": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P]),
@@ -68,6 +69,8 @@ _SIGNATURES = {
     "mvd_cast_f32_bf16": (_I, [_P, _P, _L, _P]),
     "mvd_transpose_batched": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),
     "mvd_cfg_ddpm_step_f32": (_I, [_P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _F, _P]),
+    "mvd_cfg_ddpm_step_table_f32": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P]),
+    "mvd_advance_step": (_I, [_P, _P, _P, _I, _P]),
 }
 
 

@@ -109,11 +109,22 @@ class ImageCrossAttentionProcessor(nn.Module):
         self.__dict__["_ref_cache"] = (key, kv, ref)  # hold `ref` so its storage cannot be recycled under the key
         return kv
 
+    def _gather_batch(self, kv_ref: torch.Tensor, b_ref: int, index: torch.Tensor) -> torch.Tensor:
+        key = (kv_ref.data_ptr(), index.data_ptr(), index._version)
+        cached = self.__dict__.get("_gather_cache")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        picked = kv_ref.view(b_ref, -1, kv_ref.shape[1]).index_select(0, index)
+        picked = picked.reshape(-1, kv_ref.shape[1]).contiguous()
+        self.__dict__["_gather_cache"] = (key, picked, kv_ref, index)
+        return picked
+
     # ---- the processor protocol ---------------------------------------------------------------------------
     def __call__(self, attn: Any, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None,
                  ref_hidden_states: Optional[Dict[str, torch.Tensor]] = None,
-                 residual: Optional[torch.Tensor] = None, *args, **kwargs) -> torch.Tensor:
+                 residual: Optional[torch.Tensor] = None, ref_batch_index: Optional[torch.Tensor] = None,
+                 *args, **kwargs) -> torch.Tensor:
         kwargs.pop("debug_log_file_path", None)
         native = isinstance(self.original_processor, AttnProcessor2_0)
         if ref_hidden_states is None or self.name not in ref_hidden_states:
@@ -133,7 +144,12 @@ class ImageCrossAttentionProcessor(nn.Module):
         pk = self._pack(attn)
         b, s, c = hidden_states.shape
         hs2d = hidden_states.reshape(b * s, c)
-        kv_ref = self._reference_kv(ref_hidden_states[self.name], pk)
+        ref_t = ref_hidden_states[self.name]
+        kv_ref = self._reference_kv(ref_t, pk)
+        if ref_batch_index is not None:
+            # view-sharded execution (mvd_b200/dist.py): K/V were normalised + projected over the FULL reference
+            # batch; this rank attends with the rows of its own samples
+            kv_ref = self._gather_batch(kv_ref, ref_t.shape[0], ref_batch_index)
         rows = kv_ref.shape[0]
         if rows % b:
             raise ValueError(f"{self.name}: {rows} reference tokens do not split over query batch {b}")

@@ -295,5 +295,6 @@ extern "C" int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_st
   dim3 grid((s_q + ATT_BM - 1) / ATT_BM, heads, batch);
   attn_fwd_kernel<<<grid, 192, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(mQ, mK, mV, a);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }

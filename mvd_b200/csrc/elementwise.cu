@@ -364,6 +364,35 @@ cfg_ddpm_step_kernel(const float* __restrict__ model_out, float* __restrict__ la
   latents[i] = xp;
 }
 
+
+// Device-table variant for CUDA-graph replay of the whole sampling loop: every per-step scalar is read from
+// coef_table[*step_idx] = {t, sqrt_abar, sqrt_1m_abar, c_x0, c_xt, sigma, 0, 0}; noise_table is [steps][n].
+__global__ void __launch_bounds__(256)
+cfg_ddpm_step_table_kernel(const float* __restrict__ model_out, float* __restrict__ latents,
+                           const float* __restrict__ noise_table, int64_t n, int cfg, float guidance,
+                           const float* __restrict__ coef_table, const int* __restrict__ step_idx) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int s = *step_idx;
+  const float* c = coef_table + static_cast<int64_t>(s) * 8;
+  float v = model_out[i];
+  if (cfg == 2) {
+    const float vc = model_out[n + i];
+    v = v + guidance * (vc - v);
+  }
+  const float x = latents[i];
+  const float x0 = c[1] * x - c[2] * v;
+  float xp = c[3] * x0 + c[4] * x;
+  if (noise_table != nullptr && c[5] != 0.f) xp += c[5] * noise_table[static_cast<int64_t>(s) * n + i];
+  latents[i] = xp;
+}
+__global__ void advance_step_kernel(int* step_idx, const float* coef_table, float* timestep_out, int n_steps) {
+  int s = *step_idx + 1;
+  if (s >= n_steps) s = 0;  // wrap: the loop can be replayed
+  *step_idx = s;
+  timestep_out[0] = coef_table[static_cast<int64_t>(s) * 8];
+}
+
 }  // namespace mvd
 
 extern "C" {
@@ -379,6 +408,7 @@ int mvd_film_bf16(const void* x, void* out, const float* mod, int n_img, int n_c
   film_kernel<<<dim3(bx, n_img), 256, 2 * channels * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), mod, n_cam, hw, channels, strength);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -391,6 +421,7 @@ int mvd_small_linear_f32(const float* x, int64_t ldx, const void* w, const void*
       x, ldx, static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(bias), out, ldo, M, N, K,
       silu_in, silu_out);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -402,6 +433,7 @@ int mvd_timestep_embedding_f32(const float* timesteps, int n_timesteps, float* o
   timestep_embed_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(timesteps, n_timesteps,
                                                                                             out, batch, dim);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -412,6 +444,7 @@ int mvd_camera_front_f32(const float* source_cam, const float* target_cam, float
   camera_front_kernel<<<n_views, 128, 0, static_cast<cudaStream_t>(stream)>>>(source_cam, target_cam, r_flat, t_enc,
                                                                               t_rel, n_views, pos_enc_dim, max_freq);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -431,6 +464,7 @@ int mvd_conv_in_f32_bf16(const float* latents, int n_latents, const float* mod, 
       latents, n_latents, mod, n_cam > 0 ? n_cam : 1, strength, static_cast<const __nv_bfloat16*>(w),
       static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(out), h, wdt, c_out);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -449,6 +483,7 @@ int mvd_conv_out_bf16_f32(const void* x, const void* w, const void* bias, float*
       static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
       static_cast<const __nv_bfloat16*>(bias), out, n_img, h, wdt, c_in);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -459,6 +494,7 @@ int mvd_upsample_nearest2x_bf16(const void* x, void* out, int n_img, int h, int 
   upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(x), static_cast<uint4*>(out), n_img, h, wdt, channels / 8);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -468,6 +504,7 @@ int mvd_add_bf16(const void* a, const void* b, void* out, int64_t n, void* strea
   add_kernel<<<static_cast<unsigned>((n / 8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint4*>(a), static_cast<const uint4*>(b), static_cast<uint4*>(out), n / 8);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -477,6 +514,7 @@ int mvd_cast_f32_bf16(const float* x, void* out, int64_t n, void* stream) {
   cast_f32_bf16_kernel<<<static_cast<unsigned>(((n + 1) / 2 + 255) / 256), 256, 0,
                          static_cast<cudaStream_t>(stream)>>>(x, static_cast<__nv_bfloat16*>(out), n);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -504,6 +542,7 @@ int mvd_transpose_batched(const void* x, void* out, int batch, int rows, int col
     return MVD_ERR_INVALID;
   }
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -515,6 +554,29 @@ int mvd_cfg_ddpm_step_f32(const float* model_out, float* latents, const float* n
   cfg_ddpm_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       model_out, latents, noise, n, cfg, guidance, sqrt_alpha_bar, sqrt_one_minus_alpha_bar, coef_x0, coef_xt, sigma);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
+  return MVD_OK;
+}
+
+int mvd_cfg_ddpm_step_table_f32(const float* model_out, float* latents, const float* noise_table, int64_t n, int cfg,
+                                float guidance, const float* coef_table, const int* step_idx, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(n > 0 && (cfg == 1 || cfg == 2) && coef_table != nullptr && step_idx != nullptr,
+            "cfg_ddpm_step_table: bad arguments");
+  cfg_ddpm_step_table_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      model_out, latents, noise_table, n, cfg, guidance, coef_table, step_idx);
+  MVD_CUDA(cudaGetLastError());
+  count_launches(1);
+  return MVD_OK;
+}
+
+int mvd_advance_step(int* step_idx, const float* coef_table, float* timestep_out, int n_steps, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(step_idx != nullptr && coef_table != nullptr && timestep_out != nullptr && n_steps > 0,
+            "advance_step: bad arguments");
+  advance_step_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_idx, coef_table, timestep_out, n_steps);
+  MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 

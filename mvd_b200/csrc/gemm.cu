@@ -373,6 +373,7 @@ static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUten
   int grid = args.tiles_total < sm_count() ? args.tiles_total : sm_count();
   gemm_conv_kernel<BN, S2><<<grid, 192, L::TOTAL, stream>>>(mA, mA2, mB, mO, mR, args);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 

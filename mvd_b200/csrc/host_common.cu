@@ -3,11 +3,15 @@
 #include "../../include/mvd_b200.h"
 
 #include <stdarg.h>
+#include <atomic>
 #include <mutex>
 
 namespace mvd {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -82,4 +86,5 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 extern "C" {
 const char* mvd_last_error(void) { return mvd::g_err; }
 int mvd_abi_version(void) { return MVD_ABI_VERSION; }
+int64_t mvd_kernel_launch_count(void) { return static_cast<int64_t>(mvd::g_launches.load()); }
 }

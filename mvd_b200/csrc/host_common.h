@@ -12,6 +12,7 @@ namespace mvd {
 
 void set_error(const char* fmt, ...);
 int sm_count();
+void count_launches(int n);  // bookkeeping behind mvd_kernel_launch_count()
 
 // Returns 0 on success. dims/strides innermost-first; strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,

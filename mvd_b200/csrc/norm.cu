@@ -371,11 +371,13 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
                                                               static_cast<const __nv_bfloat16*>(x2), c2, hw, groups,
                                                               workspace);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   gn_apply_kernel<<<dim3(chunks, n_img), GN_THREADS, 0, st>>>(
       static_cast<const __nv_bfloat16*>(x1), c1, static_cast<const __nv_bfloat16*>(x2), c2, hw, groups, eps, silu,
       static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), workspace, chunks,
       static_cast<__nv_bfloat16*>(out));
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -398,6 +400,7 @@ int mvd_layernorm_bf16(const void* x, int64_t ldx, const void* gamma, const void
   else
     layernorm_bf16_kernel<8><<<blocks, 256, 0, st>>>(xx, ldx, g, b, o, ldo, M, C, eps);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -408,6 +411,7 @@ int mvd_layernorm_f32(const float* x, const void* gamma, const void* beta, float
   layernorm_f32_kernel<<<(M + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(
       x, static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), out, M, C, eps, silu);
   MVD_CUDA(cudaGetLastError());
+  count_launches(1);
   return MVD_OK;
 }
 
@@ -425,6 +429,7 @@ int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels,
     MVD_CHECK(static_cast<int64_t>(batch) * channels > 1, "refnorm: unbiased std needs more than one element");
     refnorm_pixel_kernel<<<(seq + 7) / 8, 256, 0, st>>>(xx, oo, batch, seq, channels);
     MVD_CUDA(cudaGetLastError());
+  count_launches(1);
     return MVD_OK;
   }
   MVD_CHECK(workspace_floats >= mvd_refnorm_workspace_floats(channels), "refnorm: workspace too small");
@@ -446,6 +451,7 @@ int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels,
   refnorm_col_apply_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, st>>>(xx, oo, nvec, channels, mean,
                                                                                       scale);
   MVD_CUDA(cudaGetLastError());
+  count_launches(5);
   return MVD_OK;
 }
 

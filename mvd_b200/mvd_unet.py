@@ -73,6 +73,8 @@ class MultiViewUNet(nn.Module):
                                           unet_config=cfg) if use_image_conditioning else None
         self.hooks = []
         self.current_camera_embedding = None
+        # multi-GPU view sharding (mvd_b200/dist.py): dict(view0, views_local, views_total[, cfg_total, ie_text])
+        self.shard = None
         self._init_image_cross_attention()
         super().to(dtype=dtype)
 
@@ -138,6 +140,7 @@ class MultiViewUNet(nn.Module):
             self.base_unet.input_film = (mod, float(self.camera_encoder.modulation_strength))
 
         ref_hidden_states = None
+        ref_batch_index = None
         if self.use_image_conditioning and source_image_latents is not None:
             batch_size = source_image_latents.shape[0]
             ie_text = text
@@ -145,15 +148,29 @@ class MultiViewUNet(nn.Module):
                 ie_text = text[batch_size:]
             elif text.shape[0] > batch_size:
                 ie_text = text[:batch_size]
+            shard = self.shard
+            sharded = shard is not None and shard["views_local"] * shard.get("cfg_total", 2) != 0 and \
+                batch_size == shard["views_total"] and shard["views_local"] < shard["views_total"]
+            if sharded:  # features for ALL views (batch-coupled normalisation), conditional text of all views
+                ie_text = self._prepare_text(shard["ie_text"].to(device=dev), batch_size)
             features = self.image_encoder(latents=source_image_latents.to(device=dev), text_embeddings=ie_text,
                                           timestep=0)
-            if self.matched_batch_cfg and sample.shape[0] > batch_size:
-                features = self._repeat_features(features, sample.shape[0] // batch_size)
+            if sharded:
+                cfg_total = shard.get("cfg_total", 2)
+                if self.matched_batch_cfg and cfg_total > 1:
+                    features = self._repeat_features(features, cfg_total)
+                ref_batch_index = self._shard_index(shard, sample.shape[0], dev)
+            else:
+                ref_batch_index = None
+                if self.matched_batch_cfg and sample.shape[0] > batch_size:
+                    features = self._repeat_features(features, sample.shape[0] // batch_size)
             ref_hidden_states = self._map_image_features_to_attention_layers(features)
 
         kw = dict(cross_attention_kwargs or {})
         if ref_hidden_states is not None:
             kw["ref_hidden_states"] = ref_hidden_states
+            if ref_batch_index is not None:
+                kw["ref_batch_index"] = ref_batch_index
         output = self.base_unet(sample=sample, timestep=timestep, encoder_hidden_states=text, return_dict=True,
                                 timestep_cond=timestep_cond, cross_attention_kwargs=kw,
                                 added_cond_kwargs=added_cond_kwargs)
@@ -177,6 +194,20 @@ class MultiViewUNet(nn.Module):
         t = t.contiguous()
         self.__dict__["_text_cache"] = (key, t, text)
         return t
+
+    def _shard_index(self, shard, local_batch: int, dev):
+        from .dist import local_sample_index
+
+        cfg_total = shard.get("cfg_total", 2)
+        cfg_local = local_batch // shard["views_local"]
+        key = (shard["view0"], shard["views_local"], cfg_local, shard.get("cfg_branch", 0))
+        cached = self.__dict__.get("_shard_idx")
+        if cached is None or cached[0] != key:
+            idx = local_sample_index(shard["views_total"], cfg_total, shard["view0"], shard["views_local"], cfg_local,
+                                     shard.get("cfg_branch", 0))
+            cached = (key, torch.tensor(idx, device=dev, dtype=torch.long))
+            self.__dict__["_shard_idx"] = cached
+        return cached[1]
 
     def _repeat_features(self, features, times: int):
         key = (id(features), times)

@@ -407,3 +407,34 @@ def cfg_ddpm_step(model_out: torch.Tensor, latents: torch.Tensor, noise: Optiona
                                       float(sqrt_1m_abar), float(c_x0), float(c_xt), float(sigma), _stream()),
           "mvd_cfg_ddpm_step_f32")
     return latents
+
+
+def cfg_ddpm_step_table(model_out: torch.Tensor, latents: torch.Tensor, noise_table: Optional[torch.Tensor], cfg: int,
+                        guidance: float, coef_table: torch.Tensor, step_idx: torch.Tensor) -> torch.Tensor:
+    """Graph-replayable step: scalars come from coef_table[step_idx] on the device (see include/mvd_b200.h)."""
+    _contig(model_out, "model_out", F32)
+    _contig(latents, "latents", F32)
+    _contig(coef_table, "coef_table", F32)
+    _contig(step_idx, "step_idx", torch.int32)
+    n = latents.numel()
+    if model_out.numel() != cfg * n or coef_table.dim() != 2 or coef_table.shape[1] != 8:
+        raise ValueError("bad shapes for the table-driven step")
+    if noise_table is not None:
+        _contig(noise_table, "noise_table", F32)
+        if noise_table.numel() != coef_table.shape[0] * n:
+            raise ValueError("noise_table must be [steps, latents.numel()]")
+    check(lib().mvd_cfg_ddpm_step_table_f32(_p(model_out), _p(latents), _p(noise_table), n, cfg, float(guidance),
+                                            _p(coef_table), _p(step_idx), _stream()), "mvd_cfg_ddpm_step_table_f32")
+    return latents
+
+
+def advance_step(step_idx: torch.Tensor, coef_table: torch.Tensor, timestep_out: torch.Tensor) -> None:
+    _contig(step_idx, "step_idx", torch.int32)
+    _contig(coef_table, "coef_table", F32)
+    _contig(timestep_out, "timestep_out", F32)
+    check(lib().mvd_advance_step(_p(step_idx), _p(coef_table), _p(timestep_out), coef_table.shape[0], _stream()),
+          "mvd_advance_step")
+
+
+def kernel_launch_count() -> int:
+    return int(lib().mvd_kernel_launch_count())

@@ -54,7 +54,7 @@ class MVDPipeline:
                  target_camera: Optional[torch.Tensor] = None, source_images: Optional[torch.Tensor] = None,
                  ref_scale: float = 0.1, use_camera_embeddings: bool = True, use_image_conditioning: bool = True,
                  debug_log_file_path: Optional[str] = None, source_image_latents: Optional[torch.Tensor] = None,
-                 variance_noises: Optional[torch.Tensor] = None):
+                 variance_noises: Optional[torch.Tensor] = None, use_cuda_graph: bool = False):
         if prompt_embeds is None:
             raise NotImplementedError("text encoding is outside mvd_b200's scope: pass prompt_embeds [B,77,1024]")
         if source_images is not None and source_image_latents is None:
@@ -77,6 +77,18 @@ class MVDPipeline:
             source_image_latents = source_image_latents.to(dev)
             if source_image_latents.shape[0] < batch_size:  # reference :107-109
                 source_image_latents = source_image_latents.repeat(batch_size // source_image_latents.shape[0], 1, 1, 1)
+
+        if use_cuda_graph:  # whole loop on the device: one captured step replayed num_inference_steps times
+            sess = DenoiseSession(self, prompt_embeds[batch_size:] if do_cfg else prompt_embeds, num_inference_steps,
+                                  guidance_scale, prompt_embeds[:batch_size] if do_cfg else None, source_camera,
+                                  target_camera, source_image_latents, latent_size=latents.shape[-1])
+            if variance_noises is None:
+                variance_noises = torch.randn((sess.n_steps,) + tuple(latents.shape), device=dev, dtype=torch.float32,
+                                              generator=generator)
+            sess.reset(latents, variance_noises)
+            latents = sess.run().clone()
+            self.gpu_launch_count += sess.launches_per_step * sess.n_steps
+            return latents if not return_dict else {"images": latents, "latents": latents}
 
         self.scheduler.set_timesteps(num_inference_steps)
         timesteps = [int(t) for t in self.scheduler.timesteps]
@@ -105,3 +117,106 @@ class MVDPipeline:
         if not return_dict:
             return latents
         return {"images": latents, "latents": latents}
+
+
+class DenoiseSession:
+    """Device-resident sampling state of ONE object (its V views): static buffers plus, optionally, one CUDA graph
+    holding a complete denoise step — CFG duplication, MultiViewUNet forward, fused CFG + DDPM update, step-counter
+    advance — so the loop of reference pipeline.py:140-166 replays without host work.
+
+    Per-step scalars (timestep, DDPM coefficients) and the per-step variance noise are read on the device from
+    tables indexed by a device-side counter. The reference draws its positional projection on every UNet call;
+    a session pins ONE draw for its lifetime (required for replay; pass `pos_proj` to choose it)."""
+
+    def __init__(self, pipe: "MVDPipeline", prompt_embeds: torch.Tensor, num_inference_steps: int,
+                 guidance_scale: float = 1.0, negative_prompt_embeds: Optional[torch.Tensor] = None,
+                 source_camera: Optional[torch.Tensor] = None, target_camera: Optional[torch.Tensor] = None,
+                 source_image_latents: Optional[torch.Tensor] = None, latent_size: int = 64,
+                 use_cuda_graph: bool = True, pos_proj: Optional[torch.Tensor] = None, with_noise: bool = True):
+        self.pipe, self.unet, dev = pipe, pipe.unet, pipe.device
+        self.cfg = 2 if (guidance_scale > 1.0 and negative_prompt_embeds is not None) else 1
+        self.guidance = float(guidance_scale)
+        text = prompt_embeds.to(dev)
+        if self.cfg == 2:
+            text = torch.cat([negative_prompt_embeds.to(dev), text])
+        self.text = text.contiguous()
+        self.views = prompt_embeds.shape[0]
+        self.extra = {}
+        if source_camera is not None:
+            self.extra["source_camera"] = source_camera.to(dev).contiguous()
+        if target_camera is not None:
+            self.extra["target_camera"] = target_camera.to(dev).contiguous()
+        if source_image_latents is not None:
+            self.extra["source_image_latents"] = source_image_latents.to(dev).contiguous()
+        cam = getattr(self.unet, "camera_encoder", None)
+        if cam is not None and target_camera is not None and (pos_proj is not None or cam._pos_proj is None):
+            cam.set_positional_projection(pos_proj if pos_proj is not None else cam._projection(dev).float())
+        sched = pipe.scheduler
+        sched.set_timesteps(num_inference_steps)
+        self.timesteps = [int(t) for t in sched.timesteps]
+        self.n_steps = len(self.timesteps)
+        coef = torch.zeros(self.n_steps, 8)
+        for i, t in enumerate(self.timesteps):
+            coef[i, 0] = float(t)
+            coef[i, 1:6] = torch.tensor(sched.coefficients(t))
+        self.coef = coef.to(dev)
+        self.latents = torch.zeros(self.views, 4, latent_size, latent_size, device=dev, dtype=torch.float32)
+        self.noise_table = torch.zeros(self.n_steps, self.latents.numel(), device=dev, dtype=torch.float32) \
+            if with_noise else None
+        self.step_idx = torch.zeros(1, device=dev, dtype=torch.int32)
+        self.t_dev = torch.full((1,), float(self.timesteps[0]), device=dev, dtype=torch.float32)
+        self.graph = None
+        self.use_cuda_graph = use_cuda_graph
+        self.launches_per_step = 0
+
+    def reset(self, latents: torch.Tensor, variance_noises: Optional[torch.Tensor] = None):
+        """Load initial latents (and per-step noise [steps, V,4,L,L]); rewinds the step counter."""
+        self.latents.copy_(latents.to(self.latents.device, torch.float32), non_blocking=True)
+        if variance_noises is not None and self.noise_table is not None:
+            self.noise_table.copy_(variance_noises.reshape(self.n_steps, -1).to(self.noise_table.device), non_blocking=True)
+        self.step_idx.zero_()
+        self.t_dev.fill_(float(self.timesteps[0]))
+
+    def _eager_step(self):
+        inp = torch.cat([self.latents] * 2) if self.cfg == 2 else self.latents
+        out = self.unet(sample=inp, timestep=self.t_dev, encoder_hidden_states=self.text, **self.extra).sample
+        ops.cfg_ddpm_step_table(out, self.latents, self.noise_table, self.cfg, self.guidance, self.coef, self.step_idx)
+        ops.advance_step(self.step_idx, self.coef, self.t_dev)
+
+    def capture(self, warmup: int = 2):
+        """Warm every cache (weight packs, reference features, K/V) eagerly, then record one step."""
+        saved = (self.latents.clone(), self.step_idx.clone(), self.t_dev.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        before = ops.kernel_launch_count()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._eager_step()
+        self.launches_per_step = ops.kernel_launch_count() - before
+        self.latents.copy_(saved[0])
+        self.step_idx.copy_(saved[1])
+        self.t_dev.copy_(saved[2])
+        torch.cuda.synchronize()
+
+    @torch.no_grad()
+    def step(self):
+        if self.use_cuda_graph:
+            if self.graph is None:
+                self.capture()
+            self.graph.replay()
+        else:
+            before = ops.kernel_launch_count()
+            self._eager_step()
+            self.launches_per_step = ops.kernel_launch_count() - before
+
+    @torch.no_grad()
+    def run(self, steps: Optional[int] = None) -> torch.Tensor:
+        for _ in range(self.n_steps if steps is None else steps):
+            self.step()
+        return self.latents
+
