@@ -91,9 +91,8 @@ def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch:
     from mvd_b200.pipeline import DenoiseSession
 
     torch.manual_seed(0)
-    with torch.device(dev):
-        pipe = mvd_b200.create_mvd_pipeline(None, dtype=torch.bfloat16, img_ref_scale=1.0, cam_modulation_strength=1.0,
-                                            matched_batch_cfg=True, device=dev)
+    pipe = mvd_b200.create_mvd_pipeline(None, dtype=torch.bfloat16, img_ref_scale=1.0, cam_modulation_strength=1.0,
+                                        matched_batch_cfg=True, device=dev)
     g = torch.Generator(device=dev).manual_seed(1)
     with torch.no_grad():  # ref branch != original branch
         for n, p in pipe.unet.named_parameters():
@@ -205,9 +204,20 @@ def run_ours(args):
         raise SystemExit("supported GPU counts: 1, 2, 4, 8")
     from mvd_b200 import dist as mdist
     plan = mdist.shard_plan(VIEWS, CFG, world, rank)
-    pipe, sess, inp, noises = build_session(dev, plan["views_local"], plan["view0"], plan["cfg_local"], plan["cfg_branch"])
+    pipe, sess, inp, noises = build_session(dev, plan["views_local"], plan["view0"], plan["cfg_local"], plan["cfg_branch"],
+                                            use_graph=not args.profile)
     if plan["cfg_local"] == 1 and CFG == 2:
         mdist.install_cfg_pair_exchange(sess, plan, GUIDANCE)
+    if args.profile:  # one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+        for _ in range(2):
+            sess.step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        sess.step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiled_launches": sess.launches_per_step}))
+        return
     sess.capture()
     torch.cuda.synchronize()
 
@@ -327,6 +337,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

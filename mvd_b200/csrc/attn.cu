@@ -30,6 +30,12 @@ constexpr int ATT_SMEM = (1 + 2 * ATT_KS) * ATT_TILE_BYTES + 1024 + 1024;
 constexpr uint32_t TM_S0 = 0, TM_S1 = 128, TM_O = 256, TM_COLS = 512;
 constexpr float LAZY_RESCALE_THRESHOLD = 8.0f;  // log2 units: P stays below 2^8, exact in fp32/bf16 range
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnArgs {
   int Sq, Skv;
   float scale_log2;  // softmax scale * log2(e)
@@ -165,29 +171,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         tmem_ld_32x32b_x32(t_s + 96, xr + 96);
         tmem_ld_wait();
       }
-      const int valid = p.Skv - j * ATT_BN;  // columns >= valid are padding
-      float mx = -INFINITY;
+      const int valid = p.Skv - j * ATT_BN;  // columns >= valid are padding (last block only)
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (valid >= ATT_BN) {
 #pragma unroll
-      for (int c = 0; c < ATT_BN; ++c) {
-        x[c] = (c < valid) ? x[c] * p.scale_log2 : -INFINITY;
-        mx = fmaxf(mx, x[c]);
+        for (int c = 0; c < ATT_BN; c += 4) {
+          mx0 = fmaxf(mx0, x[c]);
+          mx1 = fmaxf(mx1, x[c + 1]);
+          mx2 = fmaxf(mx2, x[c + 2]);
+          mx3 = fmaxf(mx3, x[c + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < ATT_BN; ++c) {
+          x[c] = (c < valid) ? x[c] : -INFINITY;
+          mx0 = fmaxf(mx0, x[c]);
+        }
       }
+      // scores are kept raw; the softmax scale (> 0) is folded into one FFMA per element below
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
       // lazy rescale: move the reference only when the maximum grew by more than the threshold
       const bool need = mx > m_ref + LAZY_RESCALE_THRESHOLD;
       float alpha = 1.f;
       if (need) {
-        alpha = exp2f(m_ref - mx);  // 0 on the first block (m_ref = -inf)
+        alpha = ex2_approx(m_ref - mx);  // 0 on the first block (m_ref = -inf)
         m_ref = mx;
       }
-      float sum = 0.f;
+      const float neg_m = -m_ref;
+      float sum0 = 0.f, sum1 = 0.f;
       uint32_t pk[ATT_BN / 2];
 #pragma unroll
       for (int c = 0; c < ATT_BN; c += 2) {
-        const float p0 = exp2f(x[c] - m_ref);
-        const float p1 = exp2f(x[c + 1] - m_ref);
-        sum += p0 + p1;
+        const float p0 = ex2_approx(fmaf(x[c], p.scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(x[c + 1], p.scale_log2, neg_m));
+        sum0 += p0;
+        sum1 += p1;
         pk[c >> 1] = pack_bf16x2(p0, p1);
       }
+      const float sum = sum0 + sum1;
       l = l * alpha + sum;
 
       // O must not be touched (and P(j) aliases nothing PV(j-1) still reads) before PV(j-1) has finished
@@ -225,6 +246,253 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
       tmem_ld_wait();
       const float inv_l = 1.f / l;
       const int row = q_tile * ATT_BM + row_in_tile;
+      if (row < p.Sq) {
+        __nv_bfloat16* dst = p.out + static_cast<int64_t>(batch) * p.o_batch_stride +
+                             static_cast<int64_t>(row) * p.ldo + head * ATT_D;
+#pragma unroll
+        for (int c = 0; c < ATT_D; c += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
+
+// ================================================================================================
+// Two-tile variant (long sequences): one CTA owns TWO 128-row Q tiles of the same (batch, head) and two
+// softmax warpgroups. While warpgroup A runs its exponentials on S_A(j), the tensor pipe computes S_B(j) /
+// O_B += P_B V and vice versa, so the MUFU pipe (the bound for head_dim 64) never waits for the tensor pipe and
+// every K/V tile fetched by TMA is used by 256 query rows.
+//   TMEM: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)   (P aliases the first 64 columns of S)
+//   warp 0 TMA, warp 1 MMA, warps 2..5 softmax A, warps 6..9 softmax B  (320 threads)
+// MMA issue order per KV block j:  PV_A(j)  QK_A(j+1)  PV_B(j)  QK_B(j+1)   (prologue: QK_A(0) QK_B(0))
+// ================================================================================================
+constexpr int ATT2_KS = 3;
+constexpr int ATT2_SMEM = (2 + 2 * ATT2_KS) * ATT_TILE_BYTES + 1024 + 1024;
+__device__ __forceinline__ constexpr uint32_t tm2_s(int t) { return t ? 128u : 0u; }
+__device__ __forceinline__ constexpr uint32_t tm2_o(int t) { return t ? 320u : 256u; }
+
+__global__ void __launch_bounds__(320, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;  // two tiles
+  uint8_t* sK = smem + 2 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT2_KS * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT2_KS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                   // [1]
+  uint64_t* k_full = bars + 1;               // [KS]
+  uint64_t* k_empty = k_full + ATT2_KS;      // [KS]
+  uint64_t* v_full = k_empty + ATT2_KS;      // [KS]
+  uint64_t* v_empty = v_full + ATT2_KS;      // [KS]
+  uint64_t* s_full = v_empty + ATT2_KS;      // [2] per tile
+  uint64_t* p_full = s_full + 2;             // [2] per tile
+  uint64_t* o_final = p_full + 2;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x;  // rows [256 * q_pair, 256 * q_pair + 256)
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int n_blocks = (p.Skv + ATT_BN - 1) / ATT_BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATT2_KS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+    }
+    mbar_init(o_final, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+      tma_load_3d(sQ, &mapQ, q_full, head * ATT_D, q_pair * 256, batch);
+      tma_load_3d(sQ + ATT_TILE_BYTES, &mapQ, q_full, head * ATT_D, q_pair * 256 + 128, batch);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int s = j % ATT2_KS;
+        const uint32_t ph = (j / ATT2_KS) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sK + s * ATT_TILE_BYTES, &mapK, &k_full[s], head * ATT_D, j * ATT_BN, batch);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+        tma_load_3d(sV + s * ATT_TILE_BYTES, &mapV, &v_full[s], head * ATT_D, j * ATT_BN, batch);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, false, /*b_mn_major=*/true);
+      auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T ; K_j must have landed
+        const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES));
+        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (j % ATT2_KS) * ATT_TILE_BYTES));
+        const uint32_t d = tmem_base + tm2_s(t);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+        umma_commit(&s_full[t]);
+      };
+      auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
+        const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (j % ATT2_KS) * ATT_TILE_BYTES));
+        const uint32_t a_tmem = tmem_base + tm2_s(t);
+#pragma unroll
+        for (int k = 0; k < ATT_BN / 16; ++k)
+          umma_ts(tmem_base + tm2_o(t), a_tmem + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0);
+      issue_qk(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int j = 0; j < n_blocks; ++j) {
+        const int s = j % ATT2_KS;
+        const uint32_t par = j & 1;
+        const bool more = (j + 1 < n_blocks);
+        mbar_wait(&v_full[s], (j / ATT2_KS) & 1);
+        mbar_wait(&p_full[0], par);
+        tc_fence_after();
+        issue_pv(0, j);
+        if (more) {
+          mbar_wait(&k_full[(j + 1) % ATT2_KS], ((j + 1) / ATT2_KS) & 1);
+          tc_fence_after();
+          issue_qk(0, j + 1);
+        }
+        mbar_wait(&p_full[1], par);
+        tc_fence_after();
+        issue_pv(1, j);
+        umma_commit(&v_empty[s]);
+        if (more) {
+          issue_qk(1, j + 1);
+          umma_commit(&k_empty[(j + 1) % ATT2_KS]);
+        }
+      }
+      umma_commit(o_final);
+    }
+  } else {
+    // ===================== softmax warpgroups =====================
+    const int t = (warp - 2) >> 2;  // tile / warpgroup index
+    const int q = warp & 3;         // TMEM lane quadrant
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t t_s = tmem_base + tm2_s(t) + lane_off;
+    const uint32_t t_o = tmem_base + tm2_o(t) + lane_off;
+    float m_ref = -INFINITY;
+    float l = 0.f;
+
+    for (int j = 0; j < n_blocks; ++j) {
+      mbar_wait(&s_full[t], j & 1);
+      tc_fence_after();
+      float x[ATT_BN];
+      {
+        uint32_t* xr = reinterpret_cast<uint32_t*>(x);
+        tmem_ld_32x32b_x32(t_s + 0, xr + 0);
+        tmem_ld_32x32b_x32(t_s + 32, xr + 32);
+        tmem_ld_32x32b_x32(t_s + 64, xr + 64);
+        tmem_ld_32x32b_x32(t_s + 96, xr + 96);
+        tmem_ld_wait();
+      }
+      const int valid = p.Skv - j * ATT_BN;
+      float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+      if (valid >= ATT_BN) {
+#pragma unroll
+        for (int c = 0; c < ATT_BN; c += 4) {
+          mx0 = fmaxf(mx0, x[c]);
+          mx1 = fmaxf(mx1, x[c + 1]);
+          mx2 = fmaxf(mx2, x[c + 2]);
+          mx3 = fmaxf(mx3, x[c + 3]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < ATT_BN; ++c) {
+          x[c] = (c < valid) ? x[c] : -INFINITY;
+          mx0 = fmaxf(mx0, x[c]);
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      const bool need = mx > m_ref + LAZY_RESCALE_THRESHOLD;
+      float alpha = 1.f;
+      if (need) {
+        alpha = ex2_approx(m_ref - mx);
+        m_ref = mx;
+      }
+      const float neg_m = -m_ref;
+      float sum0 = 0.f, sum1 = 0.f;
+      uint32_t pk[ATT_BN / 2];
+#pragma unroll
+      for (int c = 0; c < ATT_BN; c += 2) {
+        const float p0 = ex2_approx(fmaf(x[c], p.scale_log2, neg_m));
+        const float p1 = ex2_approx(fmaf(x[c + 1], p.scale_log2, neg_m));
+        sum0 += p0;
+        sum1 += p1;
+        pk[c >> 1] = pack_bf16x2(p0, p1);
+      }
+      l = l * alpha + (sum0 + sum1);
+      // s_full(j) was committed after QK_t(j), which was issued after PV_t(j-1): O_t is quiescent here.
+      if (j > 0 && __any_sync(0xffffffffu, need)) {
+        uint32_t o[ATT_D];
+        tmem_ld_32x32b_x32(t_o, o);
+        tmem_ld_32x32b_x32(t_o + 32, o + 32);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < ATT_D; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+        tmem_st_32x32b_x32(t_o, o);
+        tmem_st_32x32b_x32(t_o + 32, o + 32);
+      }
+      tmem_st_32x32b_x32(t_s, pk);
+      tmem_st_32x32b_x32(t_s + 32, pk + 32);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[t]);
+    }
+
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    {
+      uint32_t o[ATT_D];
+      tmem_ld_32x32b_x32(t_o, o);
+      tmem_ld_32x32b_x32(t_o + 32, o + 32);
+      tmem_ld_wait();
+      const float inv_l = 1.f / l;
+      const int row = q_pair * 256 + t * 128 + row_in_tile;
       if (row < p.Sq) {
         __nv_bfloat16* dst = p.out + static_cast<int64_t>(batch) * p.o_batch_stride +
                              static_cast<int64_t>(row) * p.ldo + head * ATT_D;
@@ -290,10 +558,19 @@ extern "C" int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_st
   static bool configured = false;
   if (!configured) {
     MVD_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+    MVD_CUDA(cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
     configured = true;
   }
-  dim3 grid((s_q + ATT_BM - 1) / ATT_BM, heads, batch);
-  attn_fwd_kernel<<<grid, 192, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(mQ, mK, mV, a);
+  // long query sequences: two Q tiles per CTA (ping-pong softmax warpgroups); short ones: one tile per CTA so
+  // that small sites still spread over the SMs
+  const bool two_tiles = (s_q >= 512) && (static_cast<long>((s_q + 255) / 256) * heads * batch >= 2L * sm_count());
+  if (two_tiles) {
+    dim3 grid((s_q + 255) / 256, heads, batch);
+    attn_fwd2_kernel<<<grid, 320, ATT2_SMEM, static_cast<cudaStream_t>(stream)>>>(mQ, mK, mV, a);
+  } else {
+    dim3 grid((s_q + ATT_BM - 1) / ATT_BM, heads, batch);
+    attn_fwd_kernel<<<grid, 192, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(mQ, mK, mV, a);
+  }
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;

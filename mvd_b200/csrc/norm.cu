@@ -44,58 +44,104 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 // GroupNorm
 // ------------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
-constexpr int GN_MAX_VEC_PER_THREAD = 2;  // C <= 256 * 2 * 8 = 4096
+constexpr int GN_MAX_VPT = 2;  // 16-byte vectors per thread along C: C <= 256 * 2 * 8 = 4096
 constexpr int GN_MAX_GROUPS = 32;
+constexpr int GN_ROWS_PER_CHUNK = 32;
 
 __host__ __device__ inline int gn_chunks(int hw) {
-  int c = hw / 64;
-  return c < 1 ? 1 : (c > 64 ? 64 : c);
+  int c = (hw + GN_ROWS_PER_CHUNK - 1) / GN_ROWS_PER_CHUNK;
+  return c < 1 ? 1 : (c > 128 ? 128 : c);
+}
+
+// Thread layout shared by both kernels: block = TX x TY threads, thread (tx, ty) owns the channel vectors
+// tx, tx + TX (VPT of them) of every TY-th row of the block's row chunk: fixed channels per thread (per-channel
+// scale/shift and per-group partial sums live in registers), consecutive tx -> consecutive 16-byte vectors
+// (coalesced), 4 rows in flight per thread.
+struct GnSrc {
+  const __nv_bfloat16* base;  // first row of this image, at the thread's channel offset
+  int cs;                     // row stride (elements) of the source tensor
+};
+__device__ __forceinline__ GnSrc gn_src(const __nv_bfloat16* x1, int c1, const __nv_bfloat16* x2, int c2, int n, int hw,
+                                        int c) {
+  GnSrc s;
+  if (c < c1) {
+    s.base = x1 + static_cast<int64_t>(n) * hw * c1 + c;
+    s.cs = c1;
+  } else {
+    s.base = x2 + static_cast<int64_t>(n) * hw * c2 + (c - c1);
+    s.cs = c2;
+  }
+  return s;
 }
 
 // partial[n][chunk][g][2] = (sum, sumsq) over the chunk's rows
+template <int VPT>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
-                int groups, float* __restrict__ partial) {
+                int groups, int TX, float* __restrict__ partial) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
   const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
   const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = blockDim.x / TX;
   __shared__ float s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
   if (threadIdx.x < GN_MAX_GROUPS) {
     s_sum[threadIdx.x] = 0.f;
     s_sq[threadIdx.x] = 0.f;
   }
   __syncthreads();
-  const int nvec = C / 8;
 #pragma unroll
-  for (int i = 0; i < GN_MAX_VEC_PER_THREAD; ++i) {
-    const int v = threadIdx.x + i * GN_THREADS;
-    if (v >= nvec) break;
-    const int c = v * 8;
-    const __nv_bfloat16* base;
-    int cs, cc;
-    if (c < c1) { base = x1; cs = c1; cc = c; } else { base = x2; cs = c2; cc = c - c1; }
-    base += static_cast<int64_t>(n) * hw * cs + cc;
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (tx + i * TX) * 8;
+    if (c >= C) break;
+    const GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
     float sum[8], sq[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) sum[k] = sq[k] = 0.f;
-    for (int r = r0; r < r1; ++r) {
-      const uint4 raw = *reinterpret_cast<const uint4*>(base + static_cast<int64_t>(r) * cs);
+    int r = r0 + ty;
+    for (; r + 3 * TY < r1; r += 4 * TY) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        raw[u] = *reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r + u * TY) * src.cs);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          sum[k] += f[k];
+          sq[k] += f[k] * f[k];
+        }
+      }
+    }
+    for (; r < r1; r += TY) {
       float f[8];
-      unpack8(raw, f);
+      unpack8(*reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r) * src.cs), f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         sum[k] += f[k];
         sq[k] += f[k] * f[k];
       }
     }
+    // pre-reduce the (at most few) groups this vector touches in registers, then one smem atomic per group
+    int g_cur = c / cpg;
+    float gs = 0.f, gq = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int g = (c + k) / cpg;
-      atomicAdd(&s_sum[g], sum[k]);
-      atomicAdd(&s_sq[g], sq[k]);
+      if (g != g_cur) {
+        atomicAdd(&s_sum[g_cur], gs);
+        atomicAdd(&s_sq[g_cur], gq);
+        g_cur = g;
+        gs = gq = 0.f;
+      }
+      gs += sum[k];
+      gq += sq[k];
     }
+    atomicAdd(&s_sum[g_cur], gs);
+    atomicAdd(&s_sq[g_cur], gq);
   }
   __syncthreads();
   if (threadIdx.x < groups) {
@@ -105,42 +151,50 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
   }
 }
 
+template <int VPT>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
                 int groups, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
-                const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks,
+                const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks, int TX,
                 __nv_bfloat16* __restrict__ out) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
   const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
   const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = blockDim.x / TX;
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
-  if (threadIdx.x < groups) {
+  {
+    // groups x 8 threads reduce the per-chunk partials (fp64 combine: E[x^2] - mean^2 is cancellation-prone)
+    const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
     double s = 0.0, q = 0.0;
-    for (int k = 0; k < stat_chunks; ++k) {
-      const float* p = partial + ((static_cast<int64_t>(n) * stat_chunks + k) * groups + threadIdx.x) * 2;
-      s += p[0];
-      q += p[1];
+    if (g < groups) {
+      for (int k = part; k < stat_chunks; k += 8) {
+        const float* p = partial + ((static_cast<int64_t>(n) * stat_chunks + k) * groups + g) * 2;
+        s += p[0];
+        q += p[1];
+      }
     }
-    const double cnt = static_cast<double>(hw) * cpg;
-    const double mean = s / cnt;
-    double var = q / cnt - mean * mean;  // biased variance, as torch GroupNorm
-    if (var < 0.0) var = 0.0;
-    s_mean[threadIdx.x] = static_cast<float>(mean);
-    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (g < groups && part == 0) {
+      const double cnt = static_cast<double>(hw) * cpg;
+      const double mean = s / cnt;
+      double var = q / cnt - mean * mean;  // biased variance, as torch GroupNorm
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = static_cast<float>(mean);
+      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
   }
   __syncthreads();
-  const int nvec = C / 8;
 #pragma unroll
-  for (int i = 0; i < GN_MAX_VEC_PER_THREAD; ++i) {
-    const int v = threadIdx.x + i * GN_THREADS;
-    if (v >= nvec) break;
-    const int c = v * 8;
-    const __nv_bfloat16* base;
-    int cs, cc;
-    if (c < c1) { base = x1; cs = c1; cc = c; } else { base = x2; cs = c2; cc = c - c1; }
-    base += static_cast<int64_t>(n) * hw * cs + cc;
+  for (int i = 0; i < VPT; ++i) {
+    const int c = (tx + i * TX) * 8;
+    if (c >= C) break;
+    const GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
     __nv_bfloat16* obase = out + static_cast<int64_t>(n) * hw * C + c;
     float a[8], b[8];
     {
@@ -154,9 +208,27 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
         b[k] = bt[k] - s_mean[g] * a[k];
       }
     }
-    for (int r = r0; r < r1; ++r) {
+    int r = r0 + ty;
+    for (; r + 3 * TY < r1; r += 4 * TY) {
+      uint4 raw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        raw[u] = *reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r + u * TY) * src.cs);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(raw[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          f[k] = f[k] * a[k] + b[k];
+          if (silu) f[k] = silu_f(f[k]);
+        }
+        *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r + u * TY) * C) = pack8(f);
+      }
+    }
+    for (; r < r1; r += TY) {
       float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(base + static_cast<int64_t>(r) * cs), f);
+      unpack8(*reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r) * src.cs), f);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         f[k] = f[k] * a[k] + b[k];
@@ -362,20 +434,34 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
   if (x2 == nullptr) c2 = 0;
   MVD_CHECK(n_img > 0 && hw > 0, "groupnorm: empty problem");
   MVD_CHECK(groups > 0 && groups <= GN_MAX_GROUPS && C % groups == 0, "groupnorm: groups=%d C=%d unsupported", groups, C);
-  MVD_CHECK(c1 % 8 == 0 && c2 % 8 == 0 && C / 8 <= GN_THREADS * GN_MAX_VEC_PER_THREAD,
+  MVD_CHECK(c1 % 8 == 0 && c2 % 8 == 0 && C / 8 <= GN_THREADS * GN_MAX_VPT,
             "groupnorm: channel counts must be multiples of 8 and C <= 4096 (C=%d)", C);
   MVD_CHECK(workspace_floats >= mvd_groupnorm_workspace_floats(n_img, hw, groups), "groupnorm: workspace too small");
   const int chunks = gn_chunks(hw);
+  const int nvec = C / 8;
+  const int vpt = nvec > GN_THREADS ? 2 : 1;
+  const int TX = (nvec + vpt - 1) / vpt;
+  int TY = GN_THREADS / TX;
+  if (TY < 1) TY = 1;
+  const int threads = TX * TY;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  gn_stats_kernel<<<dim3(chunks, n_img), GN_THREADS, 0, st>>>(static_cast<const __nv_bfloat16*>(x1), c1,
-                                                              static_cast<const __nv_bfloat16*>(x2), c2, hw, groups,
-                                                              workspace);
+  auto a1 = static_cast<const __nv_bfloat16*>(x1);
+  auto a2 = static_cast<const __nv_bfloat16*>(x2);
+  if (vpt == 1)
+    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, workspace);
+  else
+    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, workspace);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
-  gn_apply_kernel<<<dim3(chunks, n_img), GN_THREADS, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(x1), c1, static_cast<const __nv_bfloat16*>(x2), c2, hw, groups, eps, silu,
-      static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), workspace, chunks,
-      static_cast<__nv_bfloat16*>(out));
+  auto gm = static_cast<const __nv_bfloat16*>(gamma);
+  auto bt = static_cast<const __nv_bfloat16*>(beta);
+  auto oo = static_cast<__nv_bfloat16*>(out);
+  if (vpt == 1)
+    gn_apply_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, eps, silu, gm, bt,
+                                                                 workspace, chunks, TX, oo);
+  else
+    gn_apply_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, eps, silu, gm, bt,
+                                                                 workspace, chunks, TX, oo);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;

@@ -270,13 +270,15 @@ def create_mvd_pipeline(pretrained_model_name_or_path=None, dtype: torch.dtype =
         device = "cuda"
     scheduler = ShiftSNRScheduler.from_scheduler(noise_scheduler=DDPMScheduler(), shift_mode="interpolated",
                                                  shift_scale=6.0, scheduler_class=DDPMScheduler)
-    mv_unet = MultiViewUNet(pretrained_model_name_or_path, dtype=dtype,
-                            use_memory_efficient_attention=use_memory_efficient_attention,
-                            enable_gradient_checkpointing=enable_gradient_checkpointing, img_ref_scale=img_ref_scale,
-                            cam_modulation_strength=cam_modulation_strength, cam_output_dim=cam_output_dim,
-                            cam_hidden_dim=cam_hidden_dim, simple_cam_encoder=simple_cam_encoder,
-                            use_camera_conditioning=use_camera_conditioning,
-                            use_image_conditioning=use_image_conditioning, matched_batch_cfg=matched_batch_cfg)
+    with torch.device(device):  # parameters are created (and initialised) directly on the GPU
+        mv_unet = MultiViewUNet(pretrained_model_name_or_path, dtype=dtype,
+                                use_memory_efficient_attention=use_memory_efficient_attention,
+                                enable_gradient_checkpointing=enable_gradient_checkpointing,
+                                img_ref_scale=img_ref_scale, cam_modulation_strength=cam_modulation_strength,
+                                cam_output_dim=cam_output_dim, cam_hidden_dim=cam_hidden_dim,
+                                simple_cam_encoder=simple_cam_encoder,
+                                use_camera_conditioning=use_camera_conditioning,
+                                use_image_conditioning=use_image_conditioning, matched_batch_cfg=matched_batch_cfg)
     mv_unet = mv_unet.to(device=device, dtype=dtype)
     pipeline = MVDPipeline(unet=mv_unet, scheduler=scheduler)
     pipeline.use_camera_conditioning = use_camera_conditioning

@@ -144,7 +144,8 @@ def _attn_ref(q, k, v, heads, scale):
 
 
 @pytest.mark.parametrize("B,heads,Sq,Skv", [(2, 5, 256, 256), (2, 20, 64, 77), (1, 10, 200, 1000), (4, 5, 4096, 4096),
-                                             (1, 5, 1024, 4 * 1024), (8, 20, 64, 64)])
+                                             (1, 5, 1024, 4 * 1024), (8, 20, 64, 64), (8, 5, 2000, 1000), (8, 10, 1024, 1024),
+                                             (8, 5, 4096, 4 * 4096 + 8)])
 @pytest.mark.parametrize("qscale", [1.0, 6.0])
 def test_attention(B, heads, Sq, Skv, qscale):
     from mvd_b200 import ops
