@@ -78,13 +78,14 @@ __device__ __forceinline__ GnSrc gn_src(const __nv_bfloat16* x1, int c1, const _
 template <int VPT>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
-                int groups, int TX, float* __restrict__ partial) {
+                int groups, int TX, int TY, float* __restrict__ partial) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
   const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
   const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = blockDim.x / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const bool active = ty < TY;  // the block is padded to whole warps
   __shared__ float s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
   if (threadIdx.x < GN_MAX_GROUPS) {
     s_sum[threadIdx.x] = 0.f;
@@ -94,7 +95,7 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = (tx + i * TX) * 8;
-    if (c >= C) break;
+    if (c >= C || !active) break;
     const GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
     float sum[8], sq[8];
 #pragma unroll
@@ -156,44 +157,48 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
                 int groups, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
                 const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks, int TX,
-                __nv_bfloat16* __restrict__ out) {
+                int TY, __nv_bfloat16* __restrict__ out) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
   const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
   const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX, TY = blockDim.x / TX;
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const bool active = ty < TY;  // the block is padded to whole warps
   __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
   {
     // groups x 8 threads reduce the per-chunk partials (fp64 combine: E[x^2] - mean^2 is cancellation-prone)
-    const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
-    double s = 0.0, q = 0.0;
-    if (g < groups) {
-      for (int k = part; k < stat_chunks; k += 8) {
-        const float* p = partial + ((static_cast<int64_t>(n) * stat_chunks + k) * groups + g) * 2;
-        s += p[0];
-        q += p[1];
+    const int part = threadIdx.x & 7;
+    for (int g0 = 0; g0 < groups; g0 += blockDim.x >> 3) {  // uniform trip count for every warp
+      const int g = g0 + (threadIdx.x >> 3);
+      double s = 0.0, q = 0.0;
+      if (g < groups) {
+        for (int k = part; k < stat_chunks; k += 8) {
+          const float* p = partial + ((static_cast<int64_t>(n) * stat_chunks + k) * groups + g) * 2;
+          s += p[0];
+          q += p[1];
+        }
       }
-    }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      s += __shfl_xor_sync(0xffffffffu, s, o);
-      q += __shfl_xor_sync(0xffffffffu, q, o);
-    }
-    if (g < groups && part == 0) {
-      const double cnt = static_cast<double>(hw) * cpg;
-      const double mean = s / cnt;
-      double var = q / cnt - mean * mean;  // biased variance, as torch GroupNorm
-      if (var < 0.0) var = 0.0;
-      s_mean[g] = static_cast<float>(mean);
-      s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      for (int o = 4; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+      }
+      if (g < groups && part == 0) {
+        const double cnt = static_cast<double>(hw) * cpg;
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;  // biased variance, as torch GroupNorm
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = static_cast<float>(mean);
+        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+      }
     }
   }
   __syncthreads();
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = (tx + i * TX) * 8;
-    if (c >= C) break;
+    if (c >= C || !active) break;
     const GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
     __nv_bfloat16* obase = out + static_cast<int64_t>(n) * hw * C + c;
     float a[8], b[8];
@@ -443,14 +448,14 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
   const int TX = (nvec + vpt - 1) / vpt;
   int TY = GN_THREADS / TX;
   if (TY < 1) TY = 1;
-  const int threads = TX * TY;
+  const int threads = (TX * TY + 31) / 32 * 32;  // whole warps; threads with ty >= TY idle in the row loops
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto a1 = static_cast<const __nv_bfloat16*>(x1);
   auto a2 = static_cast<const __nv_bfloat16*>(x2);
   if (vpt == 1)
-    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, workspace);
+    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
   else
-    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, workspace);
+    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   auto gm = static_cast<const __nv_bfloat16*>(gamma);
@@ -458,10 +463,10 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
   auto oo = static_cast<__nv_bfloat16*>(out);
   if (vpt == 1)
     gn_apply_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, eps, silu, gm, bt,
-                                                                 workspace, chunks, TX, oo);
+                                                                 workspace, chunks, TX, TY, oo);
   else
     gn_apply_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, eps, silu, gm, bt,
-                                                                 workspace, chunks, TX, oo);
+                                                                 workspace, chunks, TX, TY, oo);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
