@@ -197,18 +197,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
         alpha = ex2_approx(m_ref - mx);  // 0 on the first block (m_ref = -inf)
         m_ref = mx;
       }
-      const float neg_m = -m_ref;
-      float sum0 = 0.f, sum1 = 0.f;
+      const float2 neg_m2 = make_float2(-m_ref, -m_ref);
+      const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       uint32_t pk[ATT_BN / 2];
 #pragma unroll
-      for (int c = 0; c < ATT_BN; c += 2) {
-        const float p0 = ex2_approx(fmaf(x[c], p.scale_log2, neg_m));
-        const float p1 = ex2_approx(fmaf(x[c + 1], p.scale_log2, neg_m));
-        sum0 += p0;
-        sum1 += p1;
-        pk[c >> 1] = pack_bf16x2(p0, p1);
+      for (int c = 0; c < ATT_BN; c += 4) {  // packed FFMA2 / FADD2: 2 elements per FMA-pipe instruction
+        const float2 a0 = ffma2(make_float2(x[c], x[c + 1]), scale2, neg_m2);
+        const float2 a1 = ffma2(make_float2(x[c + 2], x[c + 3]), scale2, neg_m2);
+        const float2 e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+        const float2 e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+        acc0 = fadd2(acc0, e0);
+        acc1 = fadd2(acc1, e1);
+        pk[c >> 1] = pack_bf16x2(e0.x, e0.y);
+        pk[(c >> 1) + 1] = pack_bf16x2(e1.x, e1.y);
       }
-      const float sum = sum0 + sum1;
+      const float sum = (acc0.x + acc0.y) + (acc1.x + acc1.y);
       l = l * alpha + sum;
 
       // O must not be touched (and P(j) aliases nothing PV(j-1) still reads) before PV(j-1) has finished
@@ -277,14 +281,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 // softmax warpgroups. While warpgroup A runs its exponentials on S_A(j), the tensor pipe computes S_B(j) /
 // O_B += P_B V and vice versa, so the MUFU pipe (the bound for head_dim 64) never waits for the tensor pipe and
 // every K/V tile fetched by TMA is used by 256 query rows.
-//   TMEM: S_A [0,128)  S_B [128,256)  O_A [256,320)  O_B [320,384)   (P aliases the first 64 columns of S)
+//   TMEM: S_A [0,128) S_B [128,256) P_A [256,320) P_B [320,384) O_A [384,448) O_B [448,512)
+//   P has its OWN columns: as soon as a warpgroup has pulled S_t(j) into registers it releases S_t (s_free) and
+//   the tensor pipe refills it with S_t(j+1) while the warpgroup is still exponentiating block j — the registers
+//   act as the second S buffer, which TMEM (512 columns) has no room for at two tiles x 128 KV columns.
 //   warp 0 TMA, warp 1 MMA, warps 2..5 softmax A, warps 6..9 softmax B  (320 threads)
-// MMA issue order per KV block j:  PV_A(j)  QK_A(j+1)  PV_B(j)  QK_B(j+1)   (prologue: QK_A(0) QK_B(0))
+// MMA issue order per KV block j:  QK_A(j+1)  QK_B(j+1)  PV_A(j)  PV_B(j)   (prologue: QK_A(0) QK_B(0))
 // ================================================================================================
 constexpr int ATT2_KS = 3;
 constexpr int ATT2_SMEM = (2 + 2 * ATT2_KS) * ATT_TILE_BYTES + 1024 + 1024;
 __device__ __forceinline__ constexpr uint32_t tm2_s(int t) { return t ? 128u : 0u; }
-__device__ __forceinline__ constexpr uint32_t tm2_o(int t) { return t ? 320u : 256u; }
+__device__ __forceinline__ constexpr uint32_t tm2_p(int t) { return t ? 320u : 256u; }
+__device__ __forceinline__ constexpr uint32_t tm2_o(int t) { return t ? 448u : 384u; }
 
 __global__ void __launch_bounds__(320, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
@@ -303,9 +311,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   uint64_t* s_full = v_empty + ATT2_KS;      // [2] per tile
   uint64_t* p_full = s_full + 2;             // [2] per tile
   uint64_t* o_final = p_full + 2;            // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 1);
+  uint64_t* s_free = o_final + 1;            // [2] per tile: S_t has been read into registers
+  uint64_t* pv_done = s_free + 2;            // [2] per tile: PV_t(j) complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
   const int q_pair = blockIdx.x;  // rows [256 * q_pair, 256 * q_pair + 256)
   const int head = blockIdx.y;
@@ -326,6 +336,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     for (int t = 0; t < 2; ++t) {
       mbar_init(&s_full[t], 1);
       mbar_init(&p_full[t], 4);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&pv_done[t], 1);
     }
     mbar_init(o_final, 1);
     fence_barrier_init();
@@ -358,61 +370,79 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, false, false);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, false, /*b_mn_major=*/true);
-      auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T ; K_j must have landed
-        const uint64_t qdesc = umma_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES));
-        const uint64_t kdesc = umma_desc_sw128(smem_u32(sK + (j % ATT2_KS) * ATT_TILE_BYTES));
-        const uint32_t d = tmem_base + tm2_s(t);
+    // Warp-uniform control flow (all 32 lanes wait and compute descriptors, so they live in uniform registers and
+    // the tcgen05 operands need no per-issue R2UR traffic); one elected lane issues the MMAs and commits.
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, false, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, false, /*b_mn_major=*/true);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t q_addr = __shfl_sync(0xffffffffu, smem_u32(sQ), 0);
+    const uint32_t k_addr = __shfl_sync(0xffffffffu, smem_u32(sK), 0);
+    const uint32_t v_addr = __shfl_sync(0xffffffffu, smem_u32(sV), 0);
+    auto issue_qk = [&](int t, int j) {  // S_t = Q_t K_j^T ; K_j has landed (caller waited)
+      const uint64_t qdesc = umma_desc_sw128(q_addr + t * ATT_TILE_BYTES);
+      const uint64_t kdesc = umma_desc_sw128(k_addr + (j % ATT2_KS) * ATT_TILE_BYTES);
+      const uint32_t d = tb + tm2_s(t);
+      if (elect_one()) {
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
         umma_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
-        const uint64_t vdesc = umma_desc_sw128(smem_u32(sV + (j % ATT2_KS) * ATT_TILE_BYTES));
-        const uint32_t a_tmem = tmem_base + tm2_s(t);
-#pragma unroll
-        for (int k = 0; k < ATT_BN / 16; ++k)
-          umma_ts(tmem_base + tm2_o(t), a_tmem + 8 * k, vdesc + 128 * k, idesc_pv, (j | k) != 0);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_qk(0, 0);
-      issue_qk(1, 0);
-      umma_commit(&k_empty[0]);
-      for (int j = 0; j < n_blocks; ++j) {
-        const int s = j % ATT2_KS;
-        const uint32_t par = j & 1;
-        const bool more = (j + 1 < n_blocks);
-        mbar_wait(&v_full[s], (j / ATT2_KS) & 1);
-        mbar_wait(&p_full[0], par);
-        tc_fence_after();
-        issue_pv(0, j);
-        if (more) {
-          mbar_wait(&k_full[(j + 1) % ATT2_KS], ((j + 1) / ATT2_KS) & 1);
-          tc_fence_after();
-          issue_qk(0, j + 1);
-        }
-        mbar_wait(&p_full[1], par);
-        tc_fence_after();
-        issue_pv(1, j);
-        umma_commit(&v_empty[s]);
-        if (more) {
-          issue_qk(1, j + 1);
-          umma_commit(&k_empty[(j + 1) % ATT2_KS]);
-        }
       }
-      umma_commit(o_final);
+      __syncwarp();
+    };
+    auto issue_pv = [&](int t, int j) {  // O_t += P_t V_j
+      const uint64_t vdesc = umma_desc_sw128(v_addr + (j % ATT2_KS) * ATT_TILE_BYTES);
+      const uint32_t a_tmem = tb + tm2_p(t);
+      const uint32_t d = tb + tm2_o(t);
+      if (elect_one()) {
+        umma_ts(d, a_tmem, vdesc, idesc_pv, j != 0);
+#pragma unroll
+        for (int k = 1; k < ATT_BN / 16; ++k) umma_ts(d, a_tmem + 8 * k, vdesc + 128 * k, idesc_pv, 1);
+        umma_commit(&pv_done[t]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
+    if (elect_one()) umma_commit(&k_empty[0]);
+    __syncwarp();
+    for (int j = 0; j < n_blocks; ++j) {
+      const int s = j % ATT2_KS;
+      const uint32_t par = j & 1;
+      if (j + 1 < n_blocks) {
+        const int sn = (j + 1) % ATT2_KS;
+        mbar_wait(&k_full[sn], ((j + 1) / ATT2_KS) & 1);
+        mbar_wait(&s_free[0], par);
+        tc_fence_after();
+        issue_qk(0, j + 1);
+        mbar_wait(&s_free[1], par);
+        tc_fence_after();
+        issue_qk(1, j + 1);
+        if (elect_one()) umma_commit(&k_empty[sn]);
+        __syncwarp();
+      }
+      mbar_wait(&v_full[s], (j / ATT2_KS) & 1);
+      mbar_wait(&p_full[0], par);
+      tc_fence_after();
+      issue_pv(0, j);
+      mbar_wait(&p_full[1], par);
+      tc_fence_after();
+      issue_pv(1, j);
+      if (elect_one()) umma_commit(&v_empty[s]);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(o_final);
+    __syncwarp();
   } else {
-    // ===================== softmax warpgroups =====================
+    // ===================== softmax warpgroups (warps 2..5: tile A, 6..9: tile B) =====================
     const int t = (warp - 2) >> 2;  // tile / warpgroup index
     const int q = warp & 3;         // TMEM lane quadrant
     const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
     const int row_in_tile = q * 32 + lane;
     const uint32_t t_s = tmem_base + tm2_s(t) + lane_off;
+    const uint32_t t_p = tmem_base + tm2_p(t) + lane_off;
     const uint32_t t_o = tmem_base + tm2_o(t) + lane_off;
     float m_ref = -INFINITY;
     float l = 0.f;
@@ -429,6 +459,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         tmem_ld_32x32b_x32(t_s + 96, xr + 96);
         tmem_ld_wait();
       }
+      // S_t now lives in registers: hand the TMEM buffer back so that QK_t(j+1) overlaps this block's softmax
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
       const int valid = p.Skv - j * ATT_BN;
       float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
       if (valid >= ATT_BN) {
@@ -453,19 +487,28 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         alpha = ex2_approx(m_ref - mx);
         m_ref = mx;
       }
-      const float neg_m = -m_ref;
-      float sum0 = 0.f, sum1 = 0.f;
+      const float2 neg_m2 = make_float2(-m_ref, -m_ref);
+      const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
       uint32_t pk[ATT_BN / 2];
 #pragma unroll
-      for (int c = 0; c < ATT_BN; c += 2) {
-        const float p0 = ex2_approx(fmaf(x[c], p.scale_log2, neg_m));
-        const float p1 = ex2_approx(fmaf(x[c + 1], p.scale_log2, neg_m));
-        sum0 += p0;
-        sum1 += p1;
-        pk[c >> 1] = pack_bf16x2(p0, p1);
+      for (int c = 0; c < ATT_BN; c += 4) {  // packed FFMA2 / FADD2: 2 elements per FMA-pipe instruction
+        const float2 a0 = ffma2(make_float2(x[c], x[c + 1]), scale2, neg_m2);
+        const float2 a1 = ffma2(make_float2(x[c + 2], x[c + 3]), scale2, neg_m2);
+        const float2 e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+        const float2 e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+        acc0 = fadd2(acc0, e0);
+        acc1 = fadd2(acc1, e1);
+        pk[c >> 1] = pack_bf16x2(e0.x, e0.y);
+        pk[(c >> 1) + 1] = pack_bf16x2(e1.x, e1.y);
       }
-      l = l * alpha + (sum0 + sum1);
-      // s_full(j) was committed after QK_t(j), which was issued after PV_t(j-1): O_t is quiescent here.
+      l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+      // P_t and O_t may only be touched once PV_t(j-1) has completed (it reads P_t and accumulates into O_t);
+      // that MMA was issued a whole softmax phase ago, so this wait is normally already satisfied.
+      if (j > 0) {
+        mbar_wait(&pv_done[t], (j - 1) & 1);
+        tc_fence_after();
+      }
       if (j > 0 && __any_sync(0xffffffffu, need)) {
         uint32_t o[ATT_D];
         tmem_ld_32x32b_x32(t_o, o);
@@ -476,8 +519,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
         tmem_st_32x32b_x32(t_o, o);
         tmem_st_32x32b_x32(t_o + 32, o + 32);
       }
-      tmem_st_32x32b_x32(t_s, pk);
-      tmem_st_32x32b_x32(t_s + 32, pk + 32);
+      tmem_st_32x32b_x32(t_p, pk);
+      tmem_st_32x32b_x32(t_p + 32, pk + 32);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
