@@ -79,7 +79,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* res_bar = tmem_empty + 2;          // [4 warps][EPI_BUFS]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * EPI_BUFS);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
   const int k_blocks = p.ntaps * p.kc_per_tap;
 
@@ -148,37 +148,42 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // ===================== MMA issuer =====================
+    // Warp-uniform control flow: all lanes wait on the barriers and build the descriptors (uniform registers),
+    // one elected lane issues the tcgen05.mma / commit instructions.
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tb + acc * L::ACC_STRIDE;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * L::ACC_STRIDE;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+        const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+        const uint64_t adesc = umma_desc_sw128(sa);
+        const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+        if (elect_one()) {
+          // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
+          umma_ss(d_tmem, adesc, bdesc, idesc, kb != 0);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
-            umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
-          }
+          for (int k = 1; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
           umma_commit(&empty[stage]);
-          if (++stage == L::STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
         }
-        umma_commit(&tmem_full[acc]);
+        __syncwarp();
+        if (++stage == L::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
     }
   } else {
     // ===================== epilogue warps =====================
@@ -241,7 +246,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         // buffer (g+2)%4 was last stored by chunk g-2: allow only the newest store group to be pending
         if (lane == 0) {
-          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          // has_res: buffer (g+2)%4 (last stored by chunk g-2) is about to receive a residual slab -> at most the
+          // newest store may be pending; otherwise only buffer g%4 (chunk g-4) must be drained -> three may be.
+          if (p.has_res)
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else
+            asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
           if (p.has_res && c + 2 < n_chunks) {
             const uint32_t gb = (g + 2) % EPI_BUFS;
             mbar_arrive_expect_tx(&my_res_bar[gb], EPI_BUF_BYTES);
@@ -257,16 +267,27 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (p.bias != nullptr) {
+          if (col0 + 32 <= p.N) {  // N is a multiple of 32: a chunk is either fully inside or fully outside
+            if (p.bias != nullptr) {
+              const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);  // 64-byte aligned
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __bfloat162float(p.bias[col0 + j]);
-          }
-          if (p.img_bias != nullptr) {
-            const float* ib = p.img_bias + static_cast<size_t>(img) * p.img_bias_ld;
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const uint4 bv = __ldg(bp + q4);
+                const float2 b0 = unpack_bf16x2(bv.x), b1 = unpack_bf16x2(bv.y), b2 = unpack_bf16x2(bv.z),
+                             b3 = unpack_bf16x2(bv.w);
+                v[q4 * 8 + 0] += b0.x; v[q4 * 8 + 1] += b0.y; v[q4 * 8 + 2] += b1.x; v[q4 * 8 + 3] += b1.y;
+                v[q4 * 8 + 4] += b2.x; v[q4 * 8 + 5] += b2.y; v[q4 * 8 + 6] += b3.x; v[q4 * 8 + 7] += b3.y;
+              }
+            }
+            if (p.img_bias != nullptr) {
+              const float4* ib = reinterpret_cast<const float4*>(p.img_bias + static_cast<size_t>(img) * p.img_bias_ld +
+                                                                 col0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += ib[col0 + j];
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 f = __ldg(ib + q4);
+                v[q4 * 4 + 0] += f.x; v[q4 * 4 + 1] += f.y; v[q4 * 4 + 2] += f.z; v[q4 * 4 + 3] += f.w;
+              }
+            }
           }
         } else {
           uint32_t ra[32], rg[32];
@@ -275,13 +296,29 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tmem_ld_wait();
           const int wa = n_tile * BN + c * 32;  // permuted weight-row index of the 'a' columns
           const int wg = wa + BN / 2;
+          float ba[32], bg[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) ba[j] = bg[j] = 0.f;
+          if (p.bias != nullptr) {
+            const uint4* pa = reinterpret_cast<const uint4*>(p.bias + wa);
+            const uint4* pg = reinterpret_cast<const uint4*>(p.bias + wg);
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint4 av = __ldg(pa + q4), gv = __ldg(pg + q4);
+              const float2 a0 = unpack_bf16x2(av.x), a1 = unpack_bf16x2(av.y), a2 = unpack_bf16x2(av.z),
+                           a3 = unpack_bf16x2(av.w);
+              const float2 g0 = unpack_bf16x2(gv.x), g1 = unpack_bf16x2(gv.y), g2 = unpack_bf16x2(gv.z),
+                           g3 = unpack_bf16x2(gv.w);
+              ba[q4 * 8 + 0] = a0.x; ba[q4 * 8 + 1] = a0.y; ba[q4 * 8 + 2] = a1.x; ba[q4 * 8 + 3] = a1.y;
+              ba[q4 * 8 + 4] = a2.x; ba[q4 * 8 + 5] = a2.y; ba[q4 * 8 + 6] = a3.x; ba[q4 * 8 + 7] = a3.y;
+              bg[q4 * 8 + 0] = g0.x; bg[q4 * 8 + 1] = g0.y; bg[q4 * 8 + 2] = g1.x; bg[q4 * 8 + 3] = g1.y;
+              bg[q4 * 8 + 4] = g2.x; bg[q4 * 8 + 5] = g2.y; bg[q4 * 8 + 6] = g3.x; bg[q4 * 8 + 7] = g3.y;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float a = __uint_as_float(ra[j]), gt = __uint_as_float(rg[j]);
-            if (p.bias != nullptr) {
-              a += __bfloat162float(p.bias[wa + j]);
-              gt += __bfloat162float(p.bias[wg + j]);
-            }
+            const float a = __uint_as_float(ra[j]) + ba[j];
+            const float gt = __uint_as_float(rg[j]) + bg[j];
             v[j] = a * gelu_erf(gt);
           }
         }
@@ -424,6 +461,9 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
             "gemm/conv: pointers must be 16-byte aligned");
   MVD_CHECK(a1.pix_stride % 8 == 0 && out_pix_stride % 8 == 0 && ldw % 8 == 0,
             "gemm/conv: strides must be multiples of 8 elements");
+  MVD_CHECK((reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm/conv: bias must be 16-byte aligned");
+  MVD_CHECK(img_bias == nullptr || ((reinterpret_cast<uintptr_t>(img_bias) & 15) == 0 && img_bias_ld % 4 == 0),
+            "gemm/conv: per-image bias must be 16-byte aligned with a row stride multiple of 4");
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
