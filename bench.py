@@ -106,7 +106,7 @@ def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch:
     # couple the batch, attention.py:95-103), this rank's processors then use the rows of its own samples
     if views_local < VIEWS:
         unet.shard = dict(view0=view0, views_local=views_local, views_total=VIEWS, cfg_total=CFG, cfg_branch=cfg_branch,
-                          ie_text=inp["text"][VIEWS:])
+                          ie_text=inp["text"][VIEWS:].to(dev).contiguous())
     if cfg_local == 2:
         sess = DenoiseSession(pipe, text_c, INFER_STEPS, GUIDANCE, text_u, inp["source_camera"][vs],
                               inp["target_camera"][vs], inp["source_latents"], LATENT, use_cuda_graph=use_graph,
@@ -273,6 +273,10 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_sps = k_e2e / float(e2e_s.item())
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
     pk, how = peaks()

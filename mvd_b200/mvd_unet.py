@@ -183,16 +183,19 @@ class MultiViewUNet(nn.Module):
     def _prepare_text(self, text: torch.Tensor, batch: int) -> torch.Tensor:
         """bf16 cast + CFG repeat (mvd_unet.py:233-237), cached per text tensor (constant across steps)."""
         key = (text.data_ptr(), text._version, tuple(text.shape), text.dtype, batch)
-        cached = self.__dict__.get("_text_cache")
-        if cached is not None and cached[0] == key:
-            return cached[1]
+        cache = self.__dict__.setdefault("_text_cache", {})
+        hit = cache.get(key)
+        if hit is not None:
+            return hit[0]
         t = text
         if t.dtype != BF16:
             t = ops.cast_bf16(t.float().contiguous())
         if batch > t.shape[0]:
             t = t.repeat(batch // t.shape[0], 1, 1)
         t = t.contiguous()
-        self.__dict__["_text_cache"] = (key, t, text)
+        if len(cache) >= 8:
+            cache.clear()
+        cache[key] = (t, text)  # keep `text` alive so its data_ptr cannot be recycled under the key
         return t
 
     def _shard_index(self, shard, local_batch: int, dev):

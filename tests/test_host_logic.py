@@ -1,0 +1,82 @@
+"""CPU tests of the host-side mirror of the reference interface (no kernels are launched)."""
+import numpy as np
+import pytest
+import torch
+
+import mvd_b200
+from mvd_b200.unet import tiny_config
+
+
+def test_scheduler_tables_match_oracle():
+    from oracle.noise_schedule import DDPMOracle
+
+    s = mvd_b200.ShiftSNRScheduler.from_scheduler(mvd_b200.DDPMScheduler(), shift_mode="interpolated", shift_scale=6.0,
+                                                  scheduler_class=mvd_b200.DDPMScheduler)
+    o = DDPMOracle()
+    assert torch.equal(s.betas, o.betas)
+    s.set_timesteps(50)
+    assert s.timesteps.tolist() == o.set_timesteps(50).tolist()
+    for t in (981, 501, 21, 1):
+        assert s.coefficients(t) == o.coefficients(t)
+    with pytest.raises(ValueError):
+        mvd_b200.ShiftSNRScheduler.from_scheduler(mvd_b200.DDPMScheduler(), shift_mode="bogus")
+
+
+def test_processor_installation_and_name_maps():
+    """reference mvd_unet.py:106-162: 16 features -> 32 processors, names and state-dict keys."""
+    m = mvd_b200.MultiViewUNet(tiny_config(), dtype=torch.float32)
+    assert len(m.attention_layer_map) == 32 and len(m.feature_to_attention_map) == 16
+    assert m.feature_to_attention_map["mid_block_attn_0"] == ["mid_block_attn_0_self", "mid_block_attn_0_cross"]
+    for name, attn in m.attention_layer_map.items():
+        assert isinstance(attn.processor, mvd_b200.ImageCrossAttentionProcessor)
+        assert attn.processor.name == name and attn.processor.original_processor is not None
+    keys = set(m.state_dict().keys())
+    assert "base_unet.up_blocks.3.attentions.2.transformer_blocks.0.attn2.processor.to_k_ref.weight" in keys
+    assert "base_unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor.ref_ln.bias" in keys  # unused LN
+    assert "image_encoder.unet.mid_block.resnets.1.conv2.bias" in keys
+    assert "camera_encoder.modulators.output.3.weight" in keys and "camera_encoder.modulators.mid.0.weight" in keys
+    assert set(m.camera_encoder.modulation_hidden_dims) == {"down_0", "down_1", "down_2", "down_3", "up_0", "up_1", "up_2",
+                                                            "up_3", "mid", "output"}
+
+
+def test_weight_seeding_matches_oracle_rules():
+    """reference attention.py:199-246: self-attn k/v copied; text-attn k/v = transposed leading slice."""
+    from oracle import mv_adapter
+    from oracle.sd21_unet import Attention as OA
+    from mvd_b200.unet import Attention as PA
+
+    torch.manual_seed(0)
+    for cross in (None, 1024):
+        o = OA(320, 5, 64, cross_attention_dim=cross)
+        p = PA(320, 5, 64, cross_attention_dim=cross)
+        p.load_state_dict(o.state_dict())
+        po = mv_adapter.make_processor("x", o, 0.3)
+        pp = mvd_b200.get_attention_processor_for_module("x", p, 0.3)
+        for k, v in po.state_dict().items():
+            assert torch.equal(v, pp.state_dict()[k]), k
+        if cross:
+            assert torch.equal(pp.to_k_ref.weight, o.to_k.weight[:320, :320].t())
+
+
+def test_modulator_init_and_film_name_rules():
+    enc = mvd_b200.CameraEncoder(output_dim=1024, hidden_dim=512, modulation_hidden_dims={"down_0": 64, "mid": 128})
+    last = enc.modulators["down_0"][-1]
+    assert torch.all(last.bias[:64] == 0.5) and torch.all(last.bias[64:] == 0.0)
+    x = torch.zeros(1, 64, 2, 2)
+    assert enc.apply_modulation(x, "mid_0", torch.zeros(1, 1024)) is x        # not a modulator key: untouched
+    assert enc.apply_modulation(x, "down_0", None) is x                        # no embedding: untouched
+    assert enc._current_modulation_stats == {}
+    with pytest.raises(ValueError):
+        enc.set_positional_projection(torch.zeros(3, 3))
+
+
+def test_pipeline_scope_errors():
+    pipe = mvd_b200.MVDPipeline(unet=None, scheduler=mvd_b200.DDPMScheduler())
+    with pytest.raises(NotImplementedError, match="prompt_embeds"):
+        pipe(prompt="a chair")
+
+
+def test_cpu_forward_is_refused():
+    m = mvd_b200.MultiViewUNet(tiny_config(), dtype=torch.float32, use_image_conditioning=False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(torch.zeros(1, 4, 16, 16), 1, torch.zeros(1, 77, 64))
