@@ -346,24 +346,27 @@ transpose_bcs_kernel(const TIn* __restrict__ x, TOut* __restrict__ out, int R, i
 //   x_prev = c_x0 * x0 + c_xt * x + sigma * noise
 // model_out: fp32 [cfg * n, ...] (uncond first, cond second when cfg == 2); latents fp32 updated in place.
 // ------------------------------------------------------------------------------------------------
+// One arithmetic definition for both step kernels (no FMA contraction: bit-identical to each other, and the same
+// operation order as the scheduler's unfused fp32 tensor expressions).
+__device__ __forceinline__ float ddpm_update(float v_u, float v_c, int cfg, float guidance, float x, float sa, float sb,
+                                             float c0, float ct) {
+  float v = v_u;
+  if (cfg == 2) v = __fadd_rn(v_u, __fmul_rn(guidance, __fsub_rn(v_c, v_u)));
+  const float x0 = __fsub_rn(__fmul_rn(sa, x), __fmul_rn(sb, v));
+  return __fadd_rn(__fmul_rn(c0, x0), __fmul_rn(ct, x));
+}
+
 __global__ void __launch_bounds__(256)
 cfg_ddpm_step_kernel(const float* __restrict__ model_out, float* __restrict__ latents, const float* __restrict__ noise,
                      int64_t n, int cfg, float guidance, float sqrt_abar, float sqrt_1m_abar, float c_x0, float c_xt,
                      float sigma) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  float v = model_out[i];
-  if (cfg == 2) {
-    const float vc = model_out[n + i];
-    v = v + guidance * (vc - v);
-  }
-  const float x = latents[i];
-  const float x0 = sqrt_abar * x - sqrt_1m_abar * v;
-  float xp = c_x0 * x0 + c_xt * x;
-  if (noise != nullptr) xp += sigma * noise[i];
+  float xp = ddpm_update(model_out[i], cfg == 2 ? model_out[n + i] : 0.f, cfg, guidance, latents[i], sqrt_abar,
+                         sqrt_1m_abar, c_x0, c_xt);
+  if (noise != nullptr && sigma != 0.f) xp = __fadd_rn(xp, __fmul_rn(sigma, noise[i]));
   latents[i] = xp;
 }
-
 
 // Device-table variant for CUDA-graph replay of the whole sampling loop: every per-step scalar is read from
 // coef_table[*step_idx] = {t, sqrt_abar, sqrt_1m_abar, c_x0, c_xt, sigma, 0, 0}; noise_table is [steps][n].
@@ -375,15 +378,9 @@ cfg_ddpm_step_table_kernel(const float* __restrict__ model_out, float* __restric
   if (i >= n) return;
   const int s = *step_idx;
   const float* c = coef_table + static_cast<int64_t>(s) * 8;
-  float v = model_out[i];
-  if (cfg == 2) {
-    const float vc = model_out[n + i];
-    v = v + guidance * (vc - v);
-  }
-  const float x = latents[i];
-  const float x0 = c[1] * x - c[2] * v;
-  float xp = c[3] * x0 + c[4] * x;
-  if (noise_table != nullptr && c[5] != 0.f) xp += c[5] * noise_table[static_cast<int64_t>(s) * n + i];
+  float xp = ddpm_update(model_out[i], cfg == 2 ? model_out[n + i] : 0.f, cfg, guidance, latents[i], c[1], c[2], c[3],
+                         c[4]);
+  if (noise_table != nullptr && c[5] != 0.f) xp = __fadd_rn(xp, __fmul_rn(c[5], noise_table[static_cast<int64_t>(s) * n + i]));
   latents[i] = xp;
 }
 __global__ void advance_step_kernel(int* step_idx, const float* coef_table, float* timestep_out, int n_steps) {

@@ -86,12 +86,11 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
   const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const bool active = ty < TY;  // the block is padded to whole warps
-  __shared__ float s_sum[GN_MAX_GROUPS], s_sq[GN_MAX_GROUPS];
-  if (threadIdx.x < GN_MAX_GROUPS) {
-    s_sum[threadIdx.x] = 0.f;
-    s_sq[threadIdx.x] = 0.f;
-  }
-  __syncthreads();
+  // Deterministic reduction (no atomics): every thread parks its per-channel sums in smem, then one thread per
+  // group adds its channels x TY rows in a fixed order.
+  extern __shared__ float s_part[];  // [2][TY][C]
+  float* s_psum = s_part;
+  float* s_psq = s_part + static_cast<size_t>(TY) * C;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = (tx + i * TX) * 8;
@@ -126,29 +125,23 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
         sq[k] += f[k] * f[k];
       }
     }
-    // pre-reduce the (at most few) groups this vector touches in registers, then one smem atomic per group
-    int g_cur = c / cpg;
-    float gs = 0.f, gq = 0.f;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const int g = (c + k) / cpg;
-      if (g != g_cur) {
-        atomicAdd(&s_sum[g_cur], gs);
-        atomicAdd(&s_sq[g_cur], gq);
-        g_cur = g;
-        gs = gq = 0.f;
-      }
-      gs += sum[k];
-      gq += sq[k];
+      s_psum[static_cast<size_t>(ty) * C + c + k] = sum[k];
+      s_psq[static_cast<size_t>(ty) * C + c + k] = sq[k];
     }
-    atomicAdd(&s_sum[g_cur], gs);
-    atomicAdd(&s_sq[g_cur], gq);
   }
   __syncthreads();
   if (threadIdx.x < groups) {
+    float gs = 0.f, gq = 0.f;
+    for (int y = 0; y < TY; ++y)
+      for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
+        gs += s_psum[static_cast<size_t>(y) * C + c];
+        gq += s_psq[static_cast<size_t>(y) * C + c];
+      }
     float* p = partial + ((static_cast<int64_t>(n) * nchunks + chunk) * groups + threadIdx.x) * 2;
-    p[0] = s_sum[threadIdx.x];
-    p[1] = s_sq[threadIdx.x];
+    p[0] = gs;
+    p[1] = gq;
   }
 }
 
@@ -450,12 +443,14 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
   if (TY < 1) TY = 1;
   const int threads = (TX * TY + 31) / 32 * 32;  // whole warps; threads with ty >= TY idle in the row loops
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t stats_smem = static_cast<size_t>(2) * TY * C * sizeof(float);
+  MVD_CHECK(stats_smem <= 48 * 1024, "groupnorm: C=%d needs too much shared memory", C);
   auto a1 = static_cast<const __nv_bfloat16*>(x1);
   auto a2 = static_cast<const __nv_bfloat16*>(x2);
   if (vpt == 1)
-    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
+    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
   else
-    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
+    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   auto gm = static_cast<const __nv_bfloat16*>(gamma);

@@ -208,3 +208,32 @@ def test_cfg_ddpm_step():
     _close(out, ref, "cfg+ddpm", atol=1e-5, rtol=1e-5)
     out = ops.cfg_ddpm_step(mo[:4].contiguous(), lat.clone(), None, 1, 1.0, sa, sb, c0, ct, 0.0)
     _close(out, c0 * (sa * lat - sb * mo[:4]) + ct * lat, "ddpm no-cfg", atol=1e-5, rtol=1e-5)
+
+
+def test_cfg_ddpm_step_table_matches_scalar_variant():
+    """Device-table step (graph replay) == scalar-argument step, for every step of a 6-step schedule."""
+    import mvd_b200
+    from mvd_b200 import ops
+
+    sched = mvd_b200.ShiftSNRScheduler.from_scheduler(mvd_b200.DDPMScheduler(), shift_mode="interpolated",
+                                                      shift_scale=6.0, scheduler_class=mvd_b200.DDPMScheduler)
+    sched.set_timesteps(6)
+    ts = [int(t) for t in sched.timesteps]
+    coef = torch.zeros(len(ts), 8)
+    for i, t in enumerate(ts):
+        coef[i, 0] = float(t)
+        coef[i, 1:6] = torch.tensor(sched.coefficients(t))
+    coef = coef.cuda()
+    lat_a = _r(2, 4, 16, 16, seed=1, dtype=torch.float32)
+    lat_b = lat_a.clone()
+    noise = _r(len(ts), 2 * 4 * 16 * 16, seed=2, dtype=torch.float32)
+    step_idx = torch.zeros(1, device="cuda", dtype=torch.int32)
+    t_dev = torch.full((1,), float(ts[0]), device="cuda")
+    for i, t in enumerate(ts):
+        mo = _r(4, 4, 16, 16, seed=10 + i, dtype=torch.float32)
+        ops.cfg_ddpm_step(mo, lat_a, noise[i].view(2, 4, 16, 16).contiguous(), 2, 3.0, *sched.coefficients(t))
+        assert t_dev.item() == float(t) and step_idx.item() == i
+        ops.cfg_ddpm_step_table(mo, lat_b, noise, 2, 3.0, coef, step_idx)
+        ops.advance_step(step_idx, coef, t_dev)
+        assert torch.equal(lat_a, lat_b), f"step {i}"
+    assert step_idx.item() == 0 and t_dev.item() == float(ts[0])  # wrapped: the loop can be replayed
