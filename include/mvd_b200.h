@@ -80,8 +80,9 @@ int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_stride, const
 /* GroupNorm(groups, eps)(+SiLU) over NHWC bf16 [n_img, hw, c1(+c2)]; x2 (optional) is channel-concatenated after
  * x1 (fuses torch.cat of the up-path skip connection). out is dense [n_img, hw, c1+c2].
  * Replaces diffusers ResnetBlock2D.norm1/norm2 + nonlinearity, Transformer2DModel.norm (eps 1e-6, no SiLU) and
- * UNet2DConditionModel.conv_norm_out + conv_act. workspace: fp32 scratch of
- * mvd_groupnorm_workspace_floats() elements. */
+ * UNet2DConditionModel.conv_norm_out + conv_act. workspace: 4-byte-element scratch of
+ * mvd_groupnorm_workspace_floats() elements that MUST be zero-filled once before its first use (it starts with
+ * per-image ticket counters which the kernel re-arms itself; results are deterministic). */
 int64_t mvd_groupnorm_workspace_floats(int n_img, int hw, int groups);
 int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const void* gamma, const void* beta, void* out,
                        int n_img, int hw, int groups, float eps, int silu, float* workspace, int64_t workspace_floats,

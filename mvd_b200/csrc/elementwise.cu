@@ -73,55 +73,74 @@ film_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out
 // Used for TimestepEmbedding, all 22 ResnetBlock2D.time_emb_proj at once, and the CameraEncoder MLPs.
 // ------------------------------------------------------------------------------------------------
 constexpr int SL_MAX_M = 16;
+constexpr int SL_KTILE = 1024;  // K elements of x staged in shared memory at a time (M x 1024 fp32 = 64 KB max)
+constexpr int SL_RPW = 4;       // output features per warp (32 per block): amortises the activation staging
+template <int MT>               // MT = compile-time bound on M (register accumulators)
 __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                     const __nv_bfloat16* __restrict__ b, float* __restrict__ out, int64_t ldo, int M, int N, int K,
                     int silu_in, int silu_out) {
-  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  extern __shared__ float s_x[];  // [M][kt] activations (SiLU already applied), shared by the 8 warps of the block
+  const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * SL_RPW;
   const int lane = threadIdx.x & 31;
-  if (n >= N) return;
-  float acc[SL_MAX_M];
+  float acc[SL_RPW][MT];
 #pragma unroll
-  for (int m = 0; m < SL_MAX_M; ++m) acc[m] = 0.f;
-  const __nv_bfloat16* wr = w + static_cast<int64_t>(n) * K;
-  if ((K & 7) == 0) {
-    for (int k = lane * 8; k < K; k += 256) {
-      float wf[8];
-      ew_unpack8(*reinterpret_cast<const uint4*>(wr + k), wf);
+  for (int r = 0; r < SL_RPW; ++r)
 #pragma unroll
-      for (int m = 0; m < SL_MAX_M; ++m) {
-        if (m < M) {
-          const float* xr = x + m * ldx + k;
+    for (int m = 0; m < MT; ++m) acc[r][m] = 0.f;
+  const bool vec = (K & 7) == 0;
+  for (int k0 = 0; k0 < K; k0 += SL_KTILE) {
+    const int kt = (K - k0 < SL_KTILE) ? K - k0 : SL_KTILE;
+    __syncthreads();
+    for (int i = threadIdx.x; i < M * kt; i += blockDim.x) {
+      const int m = i / kt, k = i % kt;
+      float v = x[m * ldx + k0 + k];
+      if (silu_in) v = ew_silu(v);
+      s_x[m * kt + k] = v;
+    }
+    __syncthreads();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float xv = xr[j];
-            if (silu_in) xv = ew_silu(xv);
-            acc[m] += xv * wf[j];
+    for (int r = 0; r < SL_RPW; ++r) {
+      const int n = n0 + r;
+      if (n >= N) break;
+      const __nv_bfloat16* wr = w + static_cast<int64_t>(n) * K + k0;
+      if (vec) {
+        for (int k = lane * 8; k < kt; k += 256) {
+          float wf[8];
+          ew_unpack8(*reinterpret_cast<const uint4*>(wr + k), wf);
+#pragma unroll
+          for (int m = 0; m < MT; ++m) {
+            if (m < M) {
+              const float4 x0 = *reinterpret_cast<const float4*>(s_x + m * kt + k);
+              const float4 x1 = *reinterpret_cast<const float4*>(s_x + m * kt + k + 4);
+              acc[r][m] += x0.x * wf[0] + x0.y * wf[1] + x0.z * wf[2] + x0.w * wf[3] + x1.x * wf[4] + x1.y * wf[5] +
+                           x1.z * wf[6] + x1.w * wf[7];
+            }
           }
         }
-      }
-    }
-  } else {
-    for (int k = lane; k < K; k += 32) {
-      const float wv = __bfloat162float(wr[k]);
+      } else {
+        for (int k = lane; k < kt; k += 32) {
+          const float wv = __bfloat162float(wr[k]);
 #pragma unroll
-      for (int m = 0; m < SL_MAX_M; ++m) {
-        if (m < M) {
-          float xv = x[m * ldx + k];
-          if (silu_in) xv = ew_silu(xv);
-          acc[m] += xv * wv;
+          for (int m = 0; m < MT; ++m)
+            if (m < M) acc[r][m] += s_x[m * kt + k] * wv;
         }
       }
     }
   }
 #pragma unroll
-  for (int m = 0; m < SL_MAX_M; ++m) {
-    if (m < M) {
-      float v = ew_warp_sum(acc[m]);
-      if (lane == 0) {
-        if (b != nullptr) v += __bfloat162float(b[n]);
-        if (silu_out) v = ew_silu(v);
-        out[m * ldo + n] = v;
+  for (int r = 0; r < SL_RPW; ++r) {
+    const int n = n0 + r;
+    if (n >= N) break;
+#pragma unroll
+    for (int m = 0; m < MT; ++m) {
+      if (m < M) {
+        float v = ew_warp_sum(acc[r][m]);
+        if (lane == 0) {
+          if (b != nullptr) v += __bfloat162float(b[n]);
+          if (silu_out) v = ew_silu(v);
+          out[m * ldo + n] = v;
+        }
       }
     }
   }
@@ -187,16 +206,20 @@ __global__ void camera_front_kernel(const float* __restrict__ src, const float* 
 // fused in (src/models/mvd_unet.py:256-258 applies the "output" modulator to the input sample) and the CFG
 // duplication folded into the index (sample n reads latent n % n_lat). Output NHWC bf16.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+constexpr int CIN_ROWS = 4;  // output rows per block: the [Cout][36] weight tile in smem is reused 4 x 32 pixels
+__global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ lat, int n_lat, const float* __restrict__ mod /*[V, 8] or null*/, int V,
                float strength, const __nv_bfloat16* __restrict__ w /*[Cout, 3,3, 4]*/,
                const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int Cout) {
-  extern __shared__ float s_w[];  // [Cout][36] + bias[Cout]
+  extern __shared__ float s_w[];  // [36][Cout] (tap-major: conflict-free reads of 8 consecutive channels) + bias[Cout]
   float* s_b = s_w + Cout * 36;
-  for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) s_w[i] = __bfloat162float(w[i]);
+  for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) {
+    const int co = i / 36, tap = i % 36;
+    s_w[tap * Cout + co] = __bfloat162float(w[i]);
+  }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_b[i] = __bfloat162float(bias[i]);
-  __shared__ float s_in[4][3][34];  // 4 channels x 3 rows x (32 + 2) columns
-  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
+  __shared__ float s_in[4][CIN_ROWS + 2][34];  // 4 channels x (rows + halo) x (32 + 2) columns
+  const int n = blockIdx.z, y0 = blockIdx.y * CIN_ROWS, x0 = blockIdx.x * 32;
   float sc[4], sh[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -209,19 +232,19 @@ conv_in_kernel(const float* __restrict__ lat, int n_lat, const float* __restrict
     }
   }
   const float* lb = lat + static_cast<int64_t>(n % n_lat) * 4 * H * W;
-  for (int i = threadIdx.x; i < 4 * 3 * 34; i += blockDim.x) {
-    const int c = i / 102, r = (i / 34) % 3, col = i % 34;
-    const int yy = y + r - 1, xx = x0 + col - 1;
+  for (int i = threadIdx.x; i < 4 * (CIN_ROWS + 2) * 34; i += blockDim.x) {
+    const int c = i / ((CIN_ROWS + 2) * 34), r = (i / 34) % (CIN_ROWS + 2), col = i % 34;
+    const int yy = y0 + r - 1, xx = x0 + col - 1;
     float v = 0.f;
     if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = lb[(static_cast<int64_t>(c) * H + yy) * W + xx] * sc[c] + sh[c];
     s_in[c][r][col] = v;
   }
   __syncthreads();
-  // thread -> 8 consecutive output channels of one pixel; 32 pixels x (Cout/8) vectors per block
+  // thread -> 8 consecutive output channels of one pixel
   const int nvec = Cout / 8;
-  for (int i = threadIdx.x; i < 32 * nvec; i += blockDim.x) {
-    const int px = i / nvec, cv = (i % nvec) * 8;
-    if (x0 + px >= W) continue;
+  for (int i = threadIdx.x; i < CIN_ROWS * 32 * nvec; i += blockDim.x) {
+    const int cv = (i % nvec) * 8, px = (i / nvec) % 32, ry = i / (nvec * 32);
+    if (x0 + px >= W || y0 + ry >= H) continue;
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = s_b[cv + k];
@@ -231,11 +254,13 @@ conv_in_kernel(const float* __restrict__ lat, int n_lat, const float* __restrict
       for (int kx = 0; kx < 3; ++kx)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const float v = s_in[c][ky][px + kx];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) acc[k] += v * s_w[(cv + k) * 36 + (ky * 3 + kx) * 4 + c];
+          const float v = s_in[c][ry + ky][px + kx];
+          const float* wp = s_w + ((ky * 3 + kx) * 4 + c) * Cout + cv;
+          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
+          acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
+          acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
         }
-    *reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(n) * H + y) * W + x0 + px) * Cout + cv) = ew_pack8(acc);
+    *reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(n) * H + y0 + ry) * W + x0 + px) * Cout + cv) = ew_pack8(acc);
   }
 }
 
@@ -414,9 +439,24 @@ int mvd_small_linear_f32(const float* x, int64_t ldx, const void* w, const void*
   using namespace mvd;
   MVD_CHECK(M > 0 && M <= SL_MAX_M && N > 0 && K > 0, "small_linear: M must be in [1,16] (M=%d N=%d K=%d)", M, N, K);
   MVD_CHECK((K & 7) != 0 || ((reinterpret_cast<uintptr_t>(w) & 15) == 0), "small_linear: w must be 16-byte aligned");
-  small_linear_kernel<<<(N + 7) / 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ldx, static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(bias), out, ldo, M, N, K,
-      silu_in, silu_out);
+  const int kt = K < SL_KTILE ? K : SL_KTILE;
+  const size_t smem = static_cast<size_t>(M) * kt * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    MVD_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SL_MAX_M * SL_KTILE * static_cast<int>(sizeof(float))));
+    MVD_CUDA(cudaFuncSetAttribute(small_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  SL_MAX_M * SL_KTILE * static_cast<int>(sizeof(float))));
+    configured = true;
+  }
+  const int blocks = (N + 8 * SL_RPW - 1) / (8 * SL_RPW);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  auto ww = static_cast<const __nv_bfloat16*>(w);
+  auto bb = static_cast<const __nv_bfloat16*>(bias);
+  if (M <= 8)
+    small_linear_kernel<8><<<blocks, 256, smem, st>>>(x, ldx, ww, bb, out, ldo, M, N, K, silu_in, silu_out);
+  else
+    small_linear_kernel<16><<<blocks, 256, smem, st>>>(x, ldx, ww, bb, out, ldo, M, N, K, silu_in, silu_out);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -457,7 +497,8 @@ int mvd_conv_in_f32_bf16(const float* latents, int n_latents, const float* mod, 
     MVD_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
-  conv_in_kernel<<<dim3((wdt + 31) / 32, h, n_img), 128, smem, static_cast<cudaStream_t>(stream)>>>(
+  conv_in_kernel<<<dim3((wdt + 31) / 32, (h + CIN_ROWS - 1) / CIN_ROWS, n_img), 256, smem,
+                   static_cast<cudaStream_t>(stream)>>>(
       latents, n_latents, mod, n_cam > 0 ? n_cam : 1, strength, static_cast<const __nv_bfloat16*>(w),
       static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(out), h, wdt, c_out);
   MVD_CUDA(cudaGetLastError());

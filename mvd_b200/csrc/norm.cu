@@ -46,17 +46,24 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.f + __expf(-x))
 constexpr int GN_THREADS = 256;
 constexpr int GN_MAX_VPT = 2;  // 16-byte vectors per thread along C: C <= 256 * 2 * 8 = 4096
 constexpr int GN_MAX_GROUPS = 32;
-constexpr int GN_ROWS_PER_CHUNK = 32;
+constexpr int GN_MAX_CHUNKS = 128;
+constexpr int GN_UNROLL = 8;        // rows in flight per thread (statistics pass)
+constexpr int GN_APPLY_UNROLL = 4;  // rows in flight per thread (apply pass; keeps registers < 64)
 
-__host__ __device__ inline int gn_chunks(int hw) {
-  int c = (hw + GN_ROWS_PER_CHUNK - 1) / GN_ROWS_PER_CHUNK;
-  return c < 1 ? 1 : (c > 128 ? 128 : c);
+// chunks (blocks) per image: enough blocks to fill the machine a few times over, at least ~16 rows each
+__host__ __device__ inline int gn_chunks(int hw, int n_img, int ty) {
+  // rows per chunk ~ ty * GN_UNROLL: each thread needs about one batch of loads
+  const int rows = ty * GN_UNROLL;
+  int c = (hw + rows - 1) / rows;
+  if (c > GN_MAX_CHUNKS) c = GN_MAX_CHUNKS;
+  while (c > 1 && static_cast<long>(c) * n_img > 1184) c = (c + 1) / 2;  // <= 8 blocks per SM
+  return c < 1 ? 1 : c;
 }
 
-// Thread layout shared by both kernels: block = TX x TY threads, thread (tx, ty) owns the channel vectors
-// tx, tx + TX (VPT of them) of every TY-th row of the block's row chunk: fixed channels per thread (per-channel
-// scale/shift and per-group partial sums live in registers), consecutive tx -> consecutive 16-byte vectors
-// (coalesced), 4 rows in flight per thread.
+// Thread layout shared by both kernels: block = TX x TY threads (padded to whole warps), thread (tx, ty) owns the
+// channel vectors tx, tx + TX (VPT of them) of every TY-th row of the block's row chunk: fixed channels per thread
+// (per-channel scale/shift and partial sums live in registers), consecutive tx -> consecutive 16-byte vectors
+// (coalesced), GN_UNROLL rows in flight per thread.
 struct GnSrc {
   const __nv_bfloat16* base;  // first row of this image, at the thread's channel offset
   int cs;                     // row stride (elements) of the source tensor
@@ -74,11 +81,14 @@ __device__ __forceinline__ GnSrc gn_src(const __nv_bfloat16* x1, int c1, const _
   return s;
 }
 
-// partial[n][chunk][g][2] = (sum, sumsq) over the chunk's rows
+// Pass 1. Every block reduces its row chunk to per-group (sum, sumsq) partials (fixed order, no atomics on data);
+// the LAST block of an image to finish (ticket counter, self-resetting -> CUDA-graph safe) combines the partials of
+// all chunks in chunk order (fp64) into mean / rstd. Result: stats[n][g] = (mean, rstd). Deterministic.
 template <int VPT>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
-                int groups, int TX, int TY, float* __restrict__ partial) {
+                int groups, int TX, int TY, float eps, float* __restrict__ partial, float* __restrict__ stats,
+                unsigned int* __restrict__ tickets) {
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
@@ -86,154 +96,197 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
   const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
   const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   const bool active = ty < TY;  // the block is padded to whole warps
-  // Deterministic reduction (no atomics): every thread parks its per-channel sums in smem, then one thread per
-  // group adds its channels x TY rows in a fixed order.
   extern __shared__ float s_part[];  // [2][TY][C]
   float* s_psum = s_part;
   float* s_psq = s_part + static_cast<size_t>(TY) * C;
+  __shared__ bool s_last;
+  {
+    GnSrc src[VPT];
+    bool on[VPT];
+    float sum[VPT][8], sq[VPT][8];
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    const int c = (tx + i * TX) * 8;
-    if (c >= C || !active) break;
-    const GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
-    float sum[8], sq[8];
+    for (int i = 0; i < VPT; ++i) {
+      const int c = (tx + i * TX) * 8;
+      on[i] = active && c < C;
+      src[i] = gn_src(x1, c1, x2, c2, n, hw, on[i] ? c : 0);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sum[k] = sq[k] = 0.f;
-    int r = r0 + ty;
-    for (; r + 3 * TY < r1; r += 4 * TY) {
-      uint4 raw[4];
+      for (int k = 0; k < 8; ++k) sum[i][k] = sq[i][k] = 0.f;
+    }
+    // rows in predicated batches of GN_UNROLL, all VPT vectors of a batch together: every load of a batch is issued
+    // before any is consumed, also for the last (partial) batch — a serial loop would expose one full memory round
+    // trip per row
+    for (int r = r0 + ty; r < r1; r += GN_UNROLL * TY) {
+      uint4 raw[VPT][GN_UNROLL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        raw[u] = *reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r + u * TY) * src.cs);
+      for (int i = 0; i < VPT; ++i)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        float f[8];
-        unpack8(raw[u], f);
+        for (int u = 0; u < GN_UNROLL; ++u) {
+          const int rr = r + u * TY;
+          raw[i][u] = (on[i] && rr < r1)
+                          ? *reinterpret_cast<const uint4*>(src[i].base + static_cast<int64_t>(rr) * src[i].cs)
+                          : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+      for (int i = 0; i < VPT; ++i)
+#pragma unroll
+        for (int u = 0; u < GN_UNROLL; ++u) {
+          float f[8];
+          unpack8(raw[i][u], f);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            sum[i][k] += f[k];
+            sq[i][k] += f[k] * f[k];
+          }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      if (on[i]) {
+        const int c = (tx + i * TX) * 8;
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          sum[k] += f[k];
-          sq[k] += f[k] * f[k];
+          s_psum[static_cast<size_t>(ty) * C + c + k] = sum[i][k];
+          s_psq[static_cast<size_t>(ty) * C + c + k] = sq[i][k];
         }
       }
     }
-    for (; r < r1; r += TY) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r) * src.cs), f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        sum[k] += f[k];
-        sq[k] += f[k] * f[k];
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      s_psum[static_cast<size_t>(ty) * C + c + k] = sum[k];
-      s_psq[static_cast<size_t>(ty) * C + c + k] = sq[k];
-    }
   }
   __syncthreads();
-  if (threadIdx.x < groups) {
-    float gs = 0.f, gq = 0.f;
-    for (int y = 0; y < TY; ++y)
-      for (int c = threadIdx.x * cpg; c < (threadIdx.x + 1) * cpg; ++c) {
-        gs += s_psum[static_cast<size_t>(y) * C + c];
-        gq += s_psq[static_cast<size_t>(y) * C + c];
-      }
-    float* p = partial + ((static_cast<int64_t>(n) * nchunks + chunk) * groups + threadIdx.x) * 2;
-    p[0] = gs;
-    p[1] = gq;
-  }
-}
-
-template <int VPT>
-__global__ void __launch_bounds__(GN_THREADS)
-gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
-                int groups, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
-                const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks, int TX,
-                int TY, __nv_bfloat16* __restrict__ out) {
-  const int C = c1 + c2;
-  const int cpg = C / groups;
-  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
-  const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
-  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
-  const bool active = ty < TY;  // the block is padded to whole warps
-  __shared__ float s_mean[GN_MAX_GROUPS], s_rstd[GN_MAX_GROUPS];
   {
-    // groups x 8 threads reduce the per-chunk partials (fp64 combine: E[x^2] - mean^2 is cancellation-prone)
+    // 8 threads per group: thread (g, part) adds the channels part, part+8, ... of group g over all TY rows, then a
+    // fixed xor-shuffle tree combines the 8 parts (deterministic). blockDim is a multiple of 32; groups <= 32.
     const int part = threadIdx.x & 7;
-    for (int g0 = 0; g0 < groups; g0 += blockDim.x >> 3) {  // uniform trip count for every warp
+    for (int g0 = 0; g0 < groups; g0 += blockDim.x >> 3) {
       const int g = g0 + (threadIdx.x >> 3);
-      double s = 0.0, q = 0.0;
+      float gs = 0.f, gq = 0.f;
       if (g < groups) {
-        for (int k = part; k < stat_chunks; k += 8) {
-          const float* p = partial + ((static_cast<int64_t>(n) * stat_chunks + k) * groups + g) * 2;
-          s += p[0];
-          q += p[1];
+        for (int cc = part; cc < cpg; cc += 8) {
+          const int c = g * cpg + cc;
+          for (int y = 0; y < TY; ++y) {
+            gs += s_psum[static_cast<size_t>(y) * C + c];
+            gq += s_psq[static_cast<size_t>(y) * C + c];
+          }
         }
       }
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        q += __shfl_xor_sync(0xffffffffu, q, o);
+        gs += __shfl_xor_sync(0xffffffffu, gs, o);
+        gq += __shfl_xor_sync(0xffffffffu, gq, o);
       }
       if (g < groups && part == 0) {
-        const double cnt = static_cast<double>(hw) * cpg;
-        const double mean = s / cnt;
-        double var = q / cnt - mean * mean;  // biased variance, as torch GroupNorm
-        if (var < 0.0) var = 0.0;
-        s_mean[g] = static_cast<float>(mean);
-        s_rstd[g] = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+        float* p = partial + ((static_cast<int64_t>(n) * nchunks + chunk) * groups + g) * 2;
+        p[0] = gs;
+        p[1] = gq;
       }
     }
+    __threadfence();  // partials visible device-wide before the ticket is taken
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[n], 1u);
+    s_last = (t == static_cast<unsigned int>(nchunks) - 1u);
+    if (s_last) tickets[n] = 0u;  // re-arm for the next launch
+  }
+  __syncthreads();
+  if (s_last) {
+    // All loads of a slice are independent (issued back to back, L2-coherent __ldcg), then combined in a fixed
+    // order: slice-local chunk order, then slice order 0..7 -> deterministic regardless of which block is last.
+    __threadfence();
+    const int g = threadIdx.x & 31, slice = threadIdx.x >> 5;  // 8 slices x 32 groups (blockDim >= 256 not required)
+    const int nslices = blockDim.x >> 5;
+    double s = 0.0, q = 0.0;
+    if (g < groups) {
+      const float* pbase = partial + (static_cast<int64_t>(n) * nchunks * groups + g) * 2;
+#pragma unroll 4
+      for (int k = slice; k < nchunks; k += nslices) {
+        const float2 v = __ldcg(reinterpret_cast<const float2*>(pbase + static_cast<int64_t>(k) * groups * 2));
+        s += v.x;
+        q += v.y;
+      }
+    }
+    double* red = reinterpret_cast<double*>(s_part);  // reuse: [2][nslices][32] doubles (<= 4 KB)
+    __syncthreads();
+    red[slice * 32 + g] = s;
+    red[(nslices + slice) * 32 + g] = q;
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      double ts = 0.0, tq = 0.0;
+      for (int k = 0; k < nslices; ++k) {
+        ts += red[k * 32 + threadIdx.x];
+        tq += red[(nslices + k) * 32 + threadIdx.x];
+      }
+      const double cnt = static_cast<double>(hw) * cpg;
+      const double mean = ts / cnt;
+      double var = tq / cnt - mean * mean;  // biased variance, as torch GroupNorm
+      if (var < 0.0) var = 0.0;
+      stats[(static_cast<int64_t>(n) * groups + threadIdx.x) * 2] = static_cast<float>(mean);
+      stats[(static_cast<int64_t>(n) * groups + threadIdx.x) * 2 + 1] =
+          static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+    }
+  }
+}
+
+// Pass 2: y = (x - mean) * rstd * gamma + beta (+ SiLU), pure streaming.
+template <int VPT>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
+                int groups, int silu, const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                const float* __restrict__ stats, int TX, int TY, __nv_bfloat16* __restrict__ out) {
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int r0 = static_cast<int>(static_cast<int64_t>(hw) * chunk / nchunks);
+  const int r1 = static_cast<int>(static_cast<int64_t>(hw) * (chunk + 1) / nchunks);
+  const int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  const bool active = ty < TY;
+  GnSrc src[VPT];
+  bool on[VPT];
+  __nv_bfloat16* obase[VPT];
+  float a[VPT][8], b[VPT][8];
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
     const int c = (tx + i * TX) * 8;
-    if (c >= C || !active) break;
-    const GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
-    __nv_bfloat16* obase = out + static_cast<int64_t>(n) * hw * C + c;
-    float a[8], b[8];
-    {
-      float gm[8], bt[8];
-      unpack8(*reinterpret_cast<const uint4*>(gamma + c), gm);
-      unpack8(*reinterpret_cast<const uint4*>(beta + c), bt);
+    on[i] = active && c < C;
+    const int cc = on[i] ? c : 0;
+    src[i] = gn_src(x1, c1, x2, c2, n, hw, cc);
+    obase[i] = out + static_cast<int64_t>(n) * hw * C + cc;
+    float gm[8], bt[8];
+    unpack8(*reinterpret_cast<const uint4*>(gamma + cc), gm);
+    unpack8(*reinterpret_cast<const uint4*>(beta + cc), bt);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int g = (c + k) / cpg;
-        a[k] = gm[k] * s_rstd[g];
-        b[k] = bt[k] - s_mean[g] * a[k];
-      }
+    for (int k = 0; k < 8; ++k) {
+      const int g = (cc + k) / cpg;
+      const float mean = stats[(static_cast<int64_t>(n) * groups + g) * 2];
+      const float rstd = stats[(static_cast<int64_t>(n) * groups + g) * 2 + 1];
+      a[i][k] = gm[k] * rstd;
+      b[i][k] = bt[k] - mean * a[i][k];
     }
-    int r = r0 + ty;
-    for (; r + 3 * TY < r1; r += 4 * TY) {
-      uint4 raw[4];
+  }
+  for (int r = r0 + ty; r < r1; r += GN_APPLY_UNROLL * TY) {
+    uint4 raw[VPT][GN_APPLY_UNROLL];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        raw[u] = *reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r + u * TY) * src.cs);
+    for (int i = 0; i < VPT; ++i)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < GN_APPLY_UNROLL; ++u) {
+        const int rr = r + u * TY;
+        raw[i][u] = (on[i] && rr < r1)
+                        ? *reinterpret_cast<const uint4*>(src[i].base + static_cast<int64_t>(rr) * src[i].cs)
+                        : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+    for (int i = 0; i < VPT; ++i)
+#pragma unroll
+      for (int u = 0; u < GN_APPLY_UNROLL; ++u) {
+        const int rr = r + u * TY;
         float f[8];
-        unpack8(raw[u], f);
+        unpack8(raw[i][u], f);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          f[k] = f[k] * a[k] + b[k];
+          f[k] = f[k] * a[i][k] + b[i][k];
           if (silu) f[k] = silu_f(f[k]);
         }
-        *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r + u * TY) * C) = pack8(f);
+        if (on[i] && rr < r1) *reinterpret_cast<uint4*>(obase[i] + static_cast<int64_t>(rr) * C) = pack8(f);
       }
-    }
-    for (; r < r1; r += TY) {
-      float f[8];
-      unpack8(*reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(r) * src.cs), f);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        f[k] = f[k] * a[k] + b[k];
-        if (silu) f[k] = silu_f(f[k]);
-      }
-      *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r) * C) = pack8(f);
-    }
   }
 }
 
@@ -421,7 +474,10 @@ refnorm_col_apply_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __r
 extern "C" {
 
 int64_t mvd_groupnorm_workspace_floats(int n_img, int hw, int groups) {
-  return static_cast<int64_t>(n_img) * mvd::gn_chunks(hw) * groups * 2;
+  // [tickets: n_img uint32, padded to 64] [stats: n_img*groups*2] [partials: n_img*chunks*groups*2]
+  (void)hw;
+  return 64 + static_cast<int64_t>(n_img > 64 ? n_img : 0) + static_cast<int64_t>(n_img) * groups * 2 +
+         static_cast<int64_t>(n_img) * mvd::GN_MAX_CHUNKS * groups * 2;
 }
 
 int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const void* gamma, const void* beta, void* out,
@@ -435,33 +491,41 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
   MVD_CHECK(c1 % 8 == 0 && c2 % 8 == 0 && C / 8 <= GN_THREADS * GN_MAX_VPT,
             "groupnorm: channel counts must be multiples of 8 and C <= 4096 (C=%d)", C);
   MVD_CHECK(workspace_floats >= mvd_groupnorm_workspace_floats(n_img, hw, groups), "groupnorm: workspace too small");
-  const int chunks = gn_chunks(hw);
   const int nvec = C / 8;
   const int vpt = nvec > GN_THREADS ? 2 : 1;
   const int TX = (nvec + vpt - 1) / vpt;
   int TY = GN_THREADS / TX;
   if (TY < 1) TY = 1;
+  const int chunks = gn_chunks(hw, n_img, TY);
   const int threads = (TX * TY + 31) / 32 * 32;  // whole warps; threads with ty >= TY idle in the row loops
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const size_t stats_smem = static_cast<size_t>(2) * TY * C * sizeof(float);
+  size_t stats_smem = static_cast<size_t>(2) * TY * C * sizeof(float);
+  if (stats_smem < 2 * 8 * 32 * sizeof(double)) stats_smem = 2 * 8 * 32 * sizeof(double);
   MVD_CHECK(stats_smem <= 48 * 1024, "groupnorm: C=%d needs too much shared memory", C);
+  // workspace carve-up; the ticket counters must be zero before the FIRST use (the kernel re-arms them itself)
+  const int ticket_slots = n_img > 64 ? n_img + 64 : 64;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
+  float* stats = workspace + ticket_slots;
+  float* partial = stats + static_cast<int64_t>(n_img) * groups * 2;
   auto a1 = static_cast<const __nv_bfloat16*>(x1);
   auto a2 = static_cast<const __nv_bfloat16*>(x2);
   if (vpt == 1)
-    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
+    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, eps, partial,
+                                                                        stats, tickets);
   else
-    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, workspace);
+    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, eps, partial,
+                                                                        stats, tickets);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   auto gm = static_cast<const __nv_bfloat16*>(gamma);
   auto bt = static_cast<const __nv_bfloat16*>(beta);
   auto oo = static_cast<__nv_bfloat16*>(out);
   if (vpt == 1)
-    gn_apply_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, eps, silu, gm, bt,
-                                                                 workspace, chunks, TX, TY, oo);
+    gn_apply_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, silu, gm, bt, stats, TX, TY,
+                                                                 oo);
   else
-    gn_apply_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, eps, silu, gm, bt,
-                                                                 workspace, chunks, TX, TY, oo);
+    gn_apply_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, silu, gm, bt, stats, TX, TY,
+                                                                 oo);
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;

@@ -186,7 +186,7 @@ def _workspace(device, nfloats: int, tag: str = "ws") -> torch.Tensor:
     key = (str(device), tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nfloats:
-        ws = torch.empty(max(nfloats, 1 << 16), device=device, dtype=F32)
+        ws = torch.zeros(max(nfloats, 1 << 16), device=device, dtype=F32)  # zero: GroupNorm ticket counters
         _workspaces[key] = ws
     return ws
 
