@@ -96,6 +96,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -350,6 +352,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -609,10 +613,10 @@ extern "C" int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_st
   const bool two_tiles = (s_q >= 512) && (static_cast<long>((s_q + 255) / 256) * heads * batch >= 2L * sm_count());
   if (two_tiles) {
     dim3 grid((s_q + 255) / 256, heads, batch);
-    attn_fwd2_kernel<<<grid, 320, ATT2_SMEM, static_cast<cudaStream_t>(stream)>>>(mQ, mK, mV, a);
+    MVD_CUDA(launch_pdl(attn_fwd2_kernel, grid, dim3(320), ATT2_SMEM, static_cast<cudaStream_t>(stream), mQ, mK, mV, a));
   } else {
     dim3 grid((s_q + ATT_BM - 1) / ATT_BM, heads, batch);
-    attn_fwd_kernel<<<grid, 192, ATT_SMEM, static_cast<cudaStream_t>(stream)>>>(mQ, mK, mV, a);
+    MVD_CUDA(launch_pdl(attn_fwd_kernel, grid, dim3(192), ATT_SMEM, static_cast<cudaStream_t>(stream), mQ, mK, mV, a));
   }
   MVD_CUDA(cudaGetLastError());
   count_launches(1);

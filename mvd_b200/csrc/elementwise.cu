@@ -42,6 +42,8 @@ __device__ __forceinline__ float ew_silu(float x) { return x / (1.f + __expf(-x)
 __global__ void __launch_bounds__(256)
 film_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, const float* __restrict__ mod,
             int V, int hw, int C, float strength) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float s_coef[];  // [2][C]
   const int n = blockIdx.y;
   const float* m = mod + static_cast<int64_t>(n % V) * 2 * C;
@@ -80,6 +82,8 @@ __global__ void __launch_bounds__(256)
 small_linear_kernel(const float* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ w,
                     const __nv_bfloat16* __restrict__ b, float* __restrict__ out, int64_t ldo, int M, int N, int K,
                     int silu_in, int silu_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float s_x[];  // [M][kt] activations (SiLU already applied), shared by the 8 warps of the block
   const int n0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * SL_RPW;
   const int lane = threadIdx.x & 31;
@@ -150,6 +154,8 @@ small_linear_kernel(const float* __restrict__ x, int64_t ldx, const __nv_bfloat1
 // Timestep sinusoid (diffusers Timesteps(320, flip_sin_to_cos=True, freq_shift=0)): out[b] = [cos | sin]
 // ------------------------------------------------------------------------------------------------
 __global__ void timestep_embed_kernel(const float* __restrict__ t, int n_t, float* __restrict__ out, int B, int dim) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int half = dim / 2;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -211,6 +217,8 @@ __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ lat, int n_lat, const float* __restrict__ mod /*[V, 8] or null*/, int V,
                float strength, const __nv_bfloat16* __restrict__ w /*[Cout, 3,3, 4]*/,
                const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int Cout) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float s_w[];  // [36][Cout] (tap-major: conflict-free reads of 8 consecutive channels) + bias[Cout]
   float* s_b = s_w + Cout * 36;
   for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) {
@@ -271,6 +279,8 @@ conv_in_kernel(const float* __restrict__ lat, int n_lat, const float* __restrict
 __global__ void __launch_bounds__(256)
 conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w /*[4][3][3][Cin]*/,
                 const __nv_bfloat16* __restrict__ bias, float* __restrict__ out, int N, int H, int W, int Cin) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __nv_bfloat16 s_wo[];  // [4*9*Cin]
   for (int i = threadIdx.x; i < 36 * Cin / 8; i += blockDim.x)
     reinterpret_cast<uint4*>(s_wo)[i] = reinterpret_cast<const uint4*>(w)[i];
@@ -309,6 +319,8 @@ conv_out_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, int H, int W, int cvec) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int64_t total = static_cast<int64_t>(N) * 2 * H * 2 * W * cvec;
   if (i >= total) return;
@@ -399,6 +411,8 @@ __global__ void __launch_bounds__(256)
 cfg_ddpm_step_table_kernel(const float* __restrict__ model_out, float* __restrict__ latents,
                            const float* __restrict__ noise_table, int64_t n, int cfg, float guidance,
                            const float* __restrict__ coef_table, const int* __restrict__ step_idx) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int s = *step_idx;
@@ -409,6 +423,8 @@ cfg_ddpm_step_table_kernel(const float* __restrict__ model_out, float* __restric
   latents[i] = xp;
 }
 __global__ void advance_step_kernel(int* step_idx, const float* coef_table, float* timestep_out, int n_steps) {
+  pdl_wait();
+  pdl_launch_dependents();
   int s = *step_idx + 1;
   if (s >= n_steps) s = 0;  // wrap: the loop can be replayed
   *step_idx = s;
@@ -427,8 +443,9 @@ int mvd_film_bf16(const void* x, void* out, const float* mod, int n_img, int n_c
   int bx = static_cast<int>((static_cast<int64_t>(hw) * channels / 8 + 2047) / 2048);
   if (bx < 1) bx = 1;
   if (bx > 64) bx = 64;
-  film_kernel<<<dim3(bx, n_img), 256, 2 * channels * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<__nv_bfloat16*>(out), mod, n_cam, hw, channels, strength);
+  MVD_CUDA(launch_pdl(film_kernel, dim3(bx, n_img), dim3(256), 2 * channels * sizeof(float),
+                      static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x),
+                      static_cast<__nv_bfloat16*>(out), mod, n_cam, hw, channels, strength));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -454,9 +471,11 @@ int mvd_small_linear_f32(const float* x, int64_t ldx, const void* w, const void*
   auto ww = static_cast<const __nv_bfloat16*>(w);
   auto bb = static_cast<const __nv_bfloat16*>(bias);
   if (M <= 8)
-    small_linear_kernel<8><<<blocks, 256, smem, st>>>(x, ldx, ww, bb, out, ldo, M, N, K, silu_in, silu_out);
+    MVD_CUDA(launch_pdl(small_linear_kernel<8>, dim3(blocks), dim3(256), smem, st, x, ldx, ww, bb, out, ldo, M, N, K,
+                        silu_in, silu_out));
   else
-    small_linear_kernel<16><<<blocks, 256, smem, st>>>(x, ldx, ww, bb, out, ldo, M, N, K, silu_in, silu_out);
+    MVD_CUDA(launch_pdl(small_linear_kernel<16>, dim3(blocks), dim3(256), smem, st, x, ldx, ww, bb, out, ldo, M, N, K,
+                        silu_in, silu_out));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -467,8 +486,8 @@ int mvd_timestep_embedding_f32(const float* timesteps, int n_timesteps, float* o
   MVD_CHECK(batch > 0 && dim > 0 && dim % 2 == 0 && (n_timesteps == 1 || n_timesteps == batch),
             "timestep_embedding: bad shape");
   const int total = batch * dim / 2;
-  timestep_embed_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(timesteps, n_timesteps,
-                                                                                            out, batch, dim);
+  MVD_CUDA(launch_pdl(timestep_embed_kernel, dim3((total + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
+                      timesteps, n_timesteps, out, batch, dim));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -497,10 +516,10 @@ int mvd_conv_in_f32_bf16(const float* latents, int n_latents, const float* mod, 
     MVD_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     configured = true;
   }
-  conv_in_kernel<<<dim3((wdt + 31) / 32, (h + CIN_ROWS - 1) / CIN_ROWS, n_img), 256, smem,
-                   static_cast<cudaStream_t>(stream)>>>(
-      latents, n_latents, mod, n_cam > 0 ? n_cam : 1, strength, static_cast<const __nv_bfloat16*>(w),
-      static_cast<const __nv_bfloat16*>(bias), static_cast<__nv_bfloat16*>(out), h, wdt, c_out);
+  MVD_CUDA(launch_pdl(conv_in_kernel, dim3((wdt + 31) / 32, (h + CIN_ROWS - 1) / CIN_ROWS, n_img), dim3(256), smem,
+                      static_cast<cudaStream_t>(stream), latents, n_latents, mod, n_cam > 0 ? n_cam : 1, strength,
+                      static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(bias),
+                      static_cast<__nv_bfloat16*>(out), h, wdt, c_out));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -517,9 +536,10 @@ int mvd_conv_out_bf16_f32(const void* x, const void* w, const void* bias, float*
     configured = true;
   }
   const int64_t pix = static_cast<int64_t>(n_img) * h * wdt;
-  conv_out_kernel<<<static_cast<unsigned>((pix + 7) / 8), 256, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), static_cast<const __nv_bfloat16*>(w),
-      static_cast<const __nv_bfloat16*>(bias), out, n_img, h, wdt, c_in);
+  MVD_CUDA(launch_pdl(conv_out_kernel, dim3(static_cast<unsigned>((pix + 7) / 8)), dim3(256), smem,
+                      static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x),
+                      static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(bias), out, n_img, h, wdt,
+                      c_in));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -529,8 +549,9 @@ int mvd_upsample_nearest2x_bf16(const void* x, void* out, int n_img, int h, int 
   using namespace mvd;
   MVD_CHECK(n_img > 0 && h > 0 && wdt > 0 && channels % 8 == 0, "upsample: bad shape");
   const int64_t total = static_cast<int64_t>(n_img) * 4 * h * wdt * (channels / 8);
-  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint4*>(x), static_cast<uint4*>(out), n_img, h, wdt, channels / 8);
+  MVD_CUDA(launch_pdl(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                      static_cast<cudaStream_t>(stream), static_cast<const uint4*>(x), static_cast<uint4*>(out), n_img, h,
+                      wdt, channels / 8));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -601,8 +622,9 @@ int mvd_cfg_ddpm_step_table_f32(const float* model_out, float* latents, const fl
   using namespace mvd;
   MVD_CHECK(n > 0 && (cfg == 1 || cfg == 2) && coef_table != nullptr && step_idx != nullptr,
             "cfg_ddpm_step_table: bad arguments");
-  cfg_ddpm_step_table_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      model_out, latents, noise_table, n, cfg, guidance, coef_table, step_idx);
+  MVD_CUDA(launch_pdl(cfg_ddpm_step_table_kernel, dim3(static_cast<unsigned>((n + 255) / 256)), dim3(256), 0,
+                      static_cast<cudaStream_t>(stream), model_out, latents, noise_table, n, cfg, guidance, coef_table,
+                      step_idx));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -612,7 +634,8 @@ int mvd_advance_step(int* step_idx, const float* coef_table, float* timestep_out
   using namespace mvd;
   MVD_CHECK(step_idx != nullptr && coef_table != nullptr && timestep_out != nullptr && n_steps > 0,
             "advance_step: bad arguments");
-  advance_step_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(step_idx, coef_table, timestep_out, n_steps);
+  MVD_CUDA(launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), step_idx, coef_table,
+                      timestep_out, n_steps));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;

@@ -106,6 +106,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; from here on we read its results
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -408,7 +410,7 @@ static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUten
     configured = true;
   }
   int grid = args.tiles_total < sm_count() ? args.tiles_total : sm_count();
-  gemm_conv_kernel<BN, S2><<<grid, 192, L::TOTAL, stream>>>(mA, mA2, mB, mO, mR, args);
+  MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, S2>, dim3(grid), dim3(192), L::TOTAL, stream, mA, mA2, mB, mO, mR, args));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;

@@ -3,6 +3,7 @@
 #include "../../include/mvd_b200.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include <mutex>
 
@@ -18,6 +19,16 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MVD_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;  // measured on B200 (graph replay of the 445-launch step): 14.81 ms with PDL vs
+                                     // 14.49 ms without -> opt-in only
+  }
+  return v != 0;
 }
 
 int sm_count() {

@@ -18,6 +18,36 @@ void count_launches(int n);  // bookkeeping behind mvd_kernel_launch_count()
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, CUtensorMapSwizzle swizzle);
 
+// Programmatic dependent launch (PDL): the kernel may be scheduled while its stream predecessor is still draining;
+// every kernel launched this way executes pdl_wait() before it touches global memory (see below), so ordering and
+// visibility are exactly those of a normal stream launch, but launch latency and prologues (barrier init, TMEM
+// allocation, descriptor prefetch) overlap the predecessor's tail. Opt-in with MVD_PDL=1 (round 1 measured no gain
+// for the graph-replayed step, see host_common.cu).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+// all threads, before the first global-memory access that may depend on the previous kernel in the stream
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// allow the next kernel in the stream to be scheduled (it still waits for our completion in its own pdl_wait())
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 #define MVD_CHECK(cond, ...)          \
   do {                                \
     if (!(cond)) {                    \

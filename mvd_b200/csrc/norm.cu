@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
                 int groups, int TX, int TY, float eps, float* __restrict__ partial, float* __restrict__ stats,
                 unsigned int* __restrict__ tickets) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
@@ -232,6 +234,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
                 int groups, int silu, const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                 const float* __restrict__ stats, int TX, int TY, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = c1 + c2;
   const int cpg = C / groups;
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
@@ -298,6 +302,8 @@ __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gamma,
                       const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out, int64_t ldo, int M,
                       int C, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -510,22 +516,22 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
   auto a1 = static_cast<const __nv_bfloat16*>(x1);
   auto a2 = static_cast<const __nv_bfloat16*>(x2);
   if (vpt == 1)
-    gn_stats_kernel<1><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, eps, partial,
-                                                                        stats, tickets);
+    MVD_CUDA(launch_pdl(gn_stats_kernel<1>, dim3(chunks, n_img), dim3(threads), stats_smem, st, a1, c1, a2, c2, hw,
+                        groups, TX, TY, eps, partial, stats, tickets));
   else
-    gn_stats_kernel<2><<<dim3(chunks, n_img), threads, stats_smem, st>>>(a1, c1, a2, c2, hw, groups, TX, TY, eps, partial,
-                                                                        stats, tickets);
+    MVD_CUDA(launch_pdl(gn_stats_kernel<2>, dim3(chunks, n_img), dim3(threads), stats_smem, st, a1, c1, a2, c2, hw,
+                        groups, TX, TY, eps, partial, stats, tickets));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   auto gm = static_cast<const __nv_bfloat16*>(gamma);
   auto bt = static_cast<const __nv_bfloat16*>(beta);
   auto oo = static_cast<__nv_bfloat16*>(out);
   if (vpt == 1)
-    gn_apply_kernel<1><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, silu, gm, bt, stats, TX, TY,
-                                                                 oo);
+    MVD_CUDA(launch_pdl(gn_apply_kernel<1>, dim3(chunks, n_img), dim3(threads), 0, st, a1, c1, a2, c2, hw, groups, silu,
+                        gm, bt, stats, TX, TY, oo));
   else
-    gn_apply_kernel<2><<<dim3(chunks, n_img), threads, 0, st>>>(a1, c1, a2, c2, hw, groups, silu, gm, bt, stats, TX, TY,
-                                                                 oo);
+    MVD_CUDA(launch_pdl(gn_apply_kernel<2>, dim3(chunks, n_img), dim3(threads), 0, st, a1, c1, a2, c2, hw, groups, silu,
+                        gm, bt, stats, TX, TY, oo));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -544,11 +550,11 @@ int mvd_layernorm_bf16(const void* x, int64_t ldx, const void* gamma, const void
   auto b = static_cast<const __nv_bfloat16*>(beta);
   auto o = static_cast<__nv_bfloat16*>(out);
   if (vpl <= 2)
-    layernorm_bf16_kernel<2><<<blocks, 256, 0, st>>>(xx, ldx, g, b, o, ldo, M, C, eps);
+    MVD_CUDA(launch_pdl(layernorm_bf16_kernel<2>, dim3(blocks), dim3(256), 0, st, xx, ldx, g, b, o, ldo, M, C, eps));
   else if (vpl <= 5)
-    layernorm_bf16_kernel<5><<<blocks, 256, 0, st>>>(xx, ldx, g, b, o, ldo, M, C, eps);
+    MVD_CUDA(launch_pdl(layernorm_bf16_kernel<5>, dim3(blocks), dim3(256), 0, st, xx, ldx, g, b, o, ldo, M, C, eps));
   else
-    layernorm_bf16_kernel<8><<<blocks, 256, 0, st>>>(xx, ldx, g, b, o, ldo, M, C, eps);
+    MVD_CUDA(launch_pdl(layernorm_bf16_kernel<8>, dim3(blocks), dim3(256), 0, st, xx, ldx, g, b, o, ldo, M, C, eps));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
