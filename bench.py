@@ -12,9 +12,11 @@ processors), CFG combine + DDPM step. Reference-UNet features and their K/V are 
   value  : steps/s with everything resident in HBM; one captured CUDA graph replayed K times, CUDA events.
   e2e    : the same step through the public DenoiseSession API with HOST (pinned) latents + variance noise copied
            in and the updated latents copied out inside the timed region, every step.
-  N > 1  : strong scaling of the same object — the views (N <= 4) or view x CFG branch (N = 8) are sharded over
-           ranks, each rank normalises the (replicated, cached) reference features over the FULL batch; the only
-           per-step exchange is the CFG pair's prediction at N = 8 (NCCL all_gather of 128 KB).
+  N > 1  : `value` = sample-parallel weak scaling (configs[4]): every GPU denoises its own object, no data-path
+           collective; aggregate object-steps/s. "view_sharded" additionally reports strong scaling of ONE object
+           (configs[2]): views (N <= 4) or view x CFG branch (N = 8) sharded over ranks, reference features
+           normalised over the FULL batch on every rank; only per-step exchange = the CFG pair's prediction at N = 8
+           (NCCL all_gather of 128 KB).
 """
 from __future__ import annotations
 
@@ -83,12 +85,8 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # ours
 # ------------------------------------------------------------------------------------------------------------
-def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch: int, use_graph=True):
-    """The slice of the object this rank owns: views [view0, view0+views_local), CFG branches
-    (both if cfg_local == 2, else only `cfg_branch`: 0 = uncond, 1 = cond)."""
+def build_pipeline(dev):
     import mvd_b200
-    from helpers import synthetic_inputs
-    from mvd_b200.pipeline import DenoiseSession
 
     torch.manual_seed(0)
     pipe = mvd_b200.create_mvd_pipeline(None, dtype=torch.bfloat16, img_ref_scale=1.0, cam_modulation_strength=1.0,
@@ -98,12 +96,24 @@ def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch:
         for n, p in pipe.unet.named_parameters():
             if any(s in n for s in ("to_k_ref", "to_v_ref", "to_out_ref.0.weight")):
                 p.add_((torch.randn(p.shape, generator=g, device=dev) * 0.02).to(p.dtype))
+    return pipe
+
+
+def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch: int, use_graph=True, pipe=None):
+    """The slice of the object this rank owns: views [view0, view0+views_local), CFG branches
+    (both if cfg_local == 2, else only `cfg_branch`: 0 = uncond, 1 = cond)."""
+    from helpers import synthetic_inputs
+    from mvd_b200.pipeline import DenoiseSession
+
+    if pipe is None:
+        pipe = build_pipeline(dev)
     inp = synthetic_inputs(VIEWS, LATENT, CFG)
     vs = slice(view0, view0 + views_local)
     text_u, text_c = inp["text"][:VIEWS][vs], inp["text"][VIEWS:][vs]
     unet = pipe.unet
     # reference features are computed over ALL views on every rank (step-invariant; normalisation statistics
     # couple the batch, attention.py:95-103), this rank's processors then use the rows of its own samples
+    unet.shard = None
     if views_local < VIEWS:
         unet.shard = dict(view0=view0, views_local=views_local, views_total=VIEWS, cfg_total=CFG, cfg_branch=cfg_branch,
                           ie_text=inp["text"][VIEWS:].to(dev).contiguous())
@@ -205,11 +215,14 @@ def run_ours(args):
     if world not in (1, 2, 4, 8):
         raise SystemExit("supported GPU counts: 1, 2, 4, 8")
     from mvd_b200 import dist as mdist
-    plan = mdist.shard_plan(VIEWS, CFG, world, rank)
+    # default multi-GPU mode = sample-parallel (BASELINE.json configs[4]): every GPU denoises its OWN
+    # object (4 views x CFG 2), no data-path collective -> weak scaling; the view-sharded strong-scaling number of
+    # ONE object (configs[2]) is measured afterwards and reported under "view_sharded".
+    plan = mdist.shard_plan(VIEWS, CFG, 1, 0)
+    plan["desc"] = "single GPU" if world == 1 else \
+        f"sample-parallel x{world}: one object (4 views x CFG 2) per GPU, no data-path collective"
     pipe, sess, inp, noises = build_session(dev, plan["views_local"], plan["view0"], plan["cfg_local"], plan["cfg_branch"],
                                             use_graph=not args.profile)
-    if plan["cfg_local"] == 1 and CFG == 2:
-        mdist.install_cfg_pair_exchange(sess, plan, GUIDANCE)
     if args.profile:  # one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
         for _ in range(2):
             sess.step()
@@ -273,21 +286,51 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_sps = k_e2e / float(e2e_s.item())
+    e2e_sps = world * k_e2e / float(e2e_s.item())
 
+    # ---- strong scaling of ONE object (configs[2]): views / CFG branches sharded over the ranks
+    view_sharded = None
     if world > 1:
         import torch.distributed as dist
+        sp = mdist.shard_plan(VIEWS, CFG, world, rank)
+        k_vs = max(3, min(args.steps, 10))
+        for use_graph in (True, False):  # NCCL inside a captured step (N = 8) falls back to eager launches if needed
+            try:
+                _, s2, _, _ = build_session(dev, sp["views_local"], sp["view0"], sp["cfg_local"], sp["cfg_branch"],
+                                            use_graph=use_graph, pipe=pipe)
+                if sp["cfg_local"] == 1 and CFG == 2:
+                    mdist.install_cfg_pair_exchange(s2, sp, GUIDANCE)
+                if use_graph:
+                    s2.capture()
+                for _ in range(3):
+                    s2.step()
+                barrier()
+                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                v0.record()
+                for _ in range(k_vs):
+                    s2.step()
+                v1.record()
+                barrier()
+                vms = torch.tensor([v0.elapsed_time(v1)], device=dev)
+                dist.all_reduce(vms, op=dist.ReduceOp.MAX)
+                view_sharded = {"value": round(k_vs / (float(vms.item()) * 1e-3), 3), "unit": "steps/s of one object",
+                                "ms_per_step": round(float(vms.item()) / k_vs, 3), "scaling": "strong",
+                                "parallelism": sp["desc"], "cuda_graph": use_graph, "steps": k_vs}
+                break
+            except Exception as exc:  # noqa: BLE001
+                view_sharded = {"error": f"{type(exc).__name__}: {exc}"[:300], "cuda_graph": use_graph}
+        pipe.unet.shard = None
         dist.barrier()
         dist.destroy_process_group()
     if rank != 0:
         return
     pk, how = peaks()
-    steps_per_s = args.steps / (ms_total * 1e-3)
+    steps_per_s = world * args.steps / (ms_total * 1e-3)  # object-steps per second over all GPUs
     line = {
         "metric": "MV denoise steps/s (SD2.1+adapter 512^2, 4 views x CFG 2)", "value": round(steps_per_s, 3),
         "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
-        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "configs[1]: one SD2.1 UNet + MV-adapter denoise step, 4 views at 512^2 (64^2 latent), "
                                "CFG batch 2, bf16, random-init weights", "views": VIEWS, "cfg": CFG, "latent": LATENT,
                    "parallelism": plan["desc"], "l2": "working set (1.9 GB weights + activations) >> 126 MB L2; no flush",
@@ -295,11 +338,13 @@ def run_ours(args):
         "clocks": clocks,
         "e2e": {"value": round(e2e_sps, 3), "unit": "steps/s", "h2d_bytes_per_step": lat_host.numel() * 4 * 2,
                 "d2h_bytes_per_step": out_host.numel() * 4, "steps": k_e2e},
-        "gpu_launches": int(sess.launches_per_step * args.steps),
+        "gpu_launches": int(sess.launches_per_step * args.steps * world),
         "launches_per_step": int(sess.launches_per_step),
         "step_tflops": round(FLOPS_PER_STEP * steps_per_s / 1e12, 1),
-        "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 / pk["bf16_tflops_sustained"], 4),
+        "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 / (world * pk["bf16_tflops_sustained"]), 4),
     }
+    if view_sharded is not None:
+        line["view_sharded"] = view_sharded
     if world == 1:
         line["roofline"] = attention_roofline(dev, pk, how)
         if not args.no_cpu_baseline:
