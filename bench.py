@@ -288,10 +288,57 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_sps = world * k_e2e / float(e2e_s.item())
 
+    emitted = threading.Lock()
+
+    def emit(view_sharded):
+        if not emitted.acquire(blocking=False):  # exactly one JSON line
+            return
+        pk, how = peaks()
+        steps_per_s = world * args.steps / (ms_total * 1e-3)  # object-steps per second over all GPUs
+        line = {
+            "metric": "MV denoise steps/s (SD2.1+adapter 512^2, 4 views x CFG 2)", "value": round(steps_per_s, 3),
+            "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "configs[1]: one SD2.1 UNet + MV-adapter denoise step, 4 views at 512^2 (64^2 latent), "
+                                   "CFG batch 2, bf16, random-init weights", "views": VIEWS, "cfg": CFG, "latent": LATENT,
+                       "parallelism": plan["desc"], "l2": "working set (1.9 GB weights + activations) >> 126 MB L2; no flush",
+                       "cuda_graph": True, "step_invariant_cached": "reference-UNet features, reference/text K/V, camera emb"},
+            "clocks": clocks,
+            "e2e": {"value": round(e2e_sps, 3), "unit": "steps/s", "h2d_bytes_per_step": lat_host.numel() * 4 * 2,
+                    "d2h_bytes_per_step": out_host.numel() * 4, "steps": k_e2e},
+            "gpu_launches": int(sess.launches_per_step * args.steps * world),
+            "launches_per_step": int(sess.launches_per_step),
+            "step_tflops": round(FLOPS_PER_STEP * steps_per_s / 1e12, 1),
+            "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 / (world * pk["bf16_tflops_sustained"]), 4),
+        }
+        if view_sharded is not None:
+            line["view_sharded"] = view_sharded
+        if world == 1:
+            line["roofline"] = attention_roofline(dev, pk, how)
+            if not args.no_cpu_baseline:
+                line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line))
+        sys.stdout.flush()
+
     # ---- strong scaling of ONE object (configs[2]): views / CFG branches sharded over the ranks
     view_sharded = None
+    finished = threading.Event()
     if world > 1:
         import torch.distributed as dist
+
+        def watchdog():  # the optional section must never hang the bench: after 120 s report what we have and leave
+            if not finished.wait(120.0):
+                if rank == 0:
+                    emit({"error": "timed out after 120 s", "parallelism": "view-sharded"})
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+    run_strong = world > 1 and (world <= VIEWS or args.strong8)
+    if world > 1 and not run_strong:
+        view_sharded = {"skipped": "N = V*cfg needs a per-step NCCL exchange of the CFG pair (mvd_b200/dist.py); "
+                                   "run with --strong8 to time it"}
+    if run_strong:
         sp = mdist.shard_plan(VIEWS, CFG, world, rank)
         k_vs = max(3, min(args.steps, 10))
         for use_graph in (True, False):  # NCCL inside a captured step (N = 8) falls back to eager launches if needed
@@ -320,36 +367,16 @@ def run_ours(args):
             except Exception as exc:  # noqa: BLE001
                 view_sharded = {"error": f"{type(exc).__name__}: {exc}"[:300], "cuda_graph": use_graph}
         pipe.unet.shard = None
-        dist.barrier()
-        dist.destroy_process_group()
-    if rank != 0:
-        return
-    pk, how = peaks()
-    steps_per_s = world * args.steps / (ms_total * 1e-3)  # object-steps per second over all GPUs
-    line = {
-        "metric": "MV denoise steps/s (SD2.1+adapter 512^2, 4 views x CFG 2)", "value": round(steps_per_s, 3),
-        "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "configs[1]: one SD2.1 UNet + MV-adapter denoise step, 4 views at 512^2 (64^2 latent), "
-                               "CFG batch 2, bf16, random-init weights", "views": VIEWS, "cfg": CFG, "latent": LATENT,
-                   "parallelism": plan["desc"], "l2": "working set (1.9 GB weights + activations) >> 126 MB L2; no flush",
-                   "cuda_graph": True, "step_invariant_cached": "reference-UNet features, reference/text K/V, camera emb"},
-        "clocks": clocks,
-        "e2e": {"value": round(e2e_sps, 3), "unit": "steps/s", "h2d_bytes_per_step": lat_host.numel() * 4 * 2,
-                "d2h_bytes_per_step": out_host.numel() * 4, "steps": k_e2e},
-        "gpu_launches": int(sess.launches_per_step * args.steps * world),
-        "launches_per_step": int(sess.launches_per_step),
-        "step_tflops": round(FLOPS_PER_STEP * steps_per_s / 1e12, 1),
-        "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 / (world * pk["bf16_tflops_sustained"]), 4),
-    }
-    if view_sharded is not None:
-        line["view_sharded"] = view_sharded
-    if world == 1:
-        line["roofline"] = attention_roofline(dev, pk, how)
-        if not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
+    finished.set()
+    if rank == 0:
+        emit(view_sharded)
+    # All measurements are done and reported. Skip the NCCL teardown on purpose: destroy_process_group() after a
+    # CUDA graph that captured NCCL work has been observed to hang on this stack; leaving through os._exit is safe
+    # because nothing is left to flush but stdout.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    if world > 1:
+        os._exit(0)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -383,6 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong8", action="store_true", help="also time the view x CFG sharded mode at 8 GPUs")
     ap.add_argument("--profile", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":
