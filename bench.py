@@ -163,7 +163,7 @@ def attention_roofline(dev, pk, how):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
-    return {"kernel": "attn_fwd_kernel (B=8,h=5,Sq=Skv=4096,d=64)", "bound": "tensor", "achieved": round(achieved, 1),
+    return {"kernel": "attn_fwd2_kernel (B=8,h=5,Sq=Skv=4096,d=64)", "bound": "tensor", "achieved": round(achieved, 1),
             "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
             "peak_source": f"{how} burst bf16 GEMM", "ms_per_launch": round(ms, 4),
             "flops_per_launch": flops}

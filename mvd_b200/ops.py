@@ -182,8 +182,9 @@ _workspaces: dict = {}
 
 
 def _workspace(device, nfloats: int, tag: str = "ws") -> torch.Tensor:
-    """Persistent fp32 scratch per (device, tag) — stable addresses, CUDA-graph friendly."""
-    key = (str(device), tag)
+    """Persistent zero-initialised fp32 scratch per (device, stream, tag): stable addresses (CUDA-graph friendly) and
+    never shared between streams that could run concurrently (GroupNorm keeps ticket counters in it)."""
+    key = (str(device), _stream(), tag)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nfloats:
         ws = torch.zeros(max(nfloats, 1 << 16), device=device, dtype=F32)  # zero: GroupNorm ticket counters

@@ -172,3 +172,23 @@ def test_attention_strided_fused_qkv():
     _cmp(cat[:, :, C:], _attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), heads, 0.125), "attn strided",
          atol=1.5e-2)
     assert cat[:, :, :C].abs().max().item() == 0
+
+
+def test_attention_config3_cross_view_length():
+    """configs[3] top site: one 96x96 view (9216 queries) attending over all 8 views' tokens (S_kv = 73,728), 5 heads.
+    Reference computed in fp32 by query chunks (the full score matrix would be 13.6 GB)."""
+    from mvd_b200 import ops
+
+    heads, Sq, Skv = 5, 9216, 8 * 9216
+    C = heads * 64
+    q, k, v = _randn(1, Sq, C, seed=1), _randn(1, Skv, C, seed=2), _randn(1, Skv, C, seed=3)
+    out = ops.attention(q, k, v, heads)
+    torch.cuda.synchronize()
+    kh = k.float().view(1, Skv, heads, 64).transpose(1, 2)
+    vh = v.float().view(1, Skv, heads, 64).transpose(1, 2)
+    ref = torch.empty(1, Sq, C, device="cuda")
+    for s in range(0, Sq, 1024):
+        qh = q[:, s:s + 1024].float().view(1, -1, heads, 64).transpose(1, 2)
+        p = torch.softmax(qh @ kh.transpose(-1, -2) * 0.125, dim=-1)
+        ref[:, s:s + 1024] = (p @ vh).transpose(1, 2).reshape(1, -1, C)
+    _cmp(out, ref, "attn 9216 x 73728 (configs[3])", atol=2e-3)
