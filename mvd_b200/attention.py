@@ -16,6 +16,7 @@ concatenated, plus any injected rows) goes through the same kernels (north-star 
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, Optional
 
 import torch
@@ -27,6 +28,20 @@ from .unet import BF16, AttnProcessor2_0, _bf16, _versions, nhwc_view
 
 def log_debug(file_path, message):  # reference src/utils.py:25-34; callers here never build tensor f-strings
     return None
+
+
+# Run the reference-attention branch concurrently with the original branch (second CUDA stream, fork/join by events).
+# MVD_OVERLAP_BRANCHES=0 launches them back to back on the current stream instead.
+OVERLAP_BRANCHES = os.environ.get("MVD_OVERLAP_BRANCHES", "1") != "0"
+_branch_streams: Dict[int, "torch.cuda.Stream"] = {}
+
+
+def _branch_stream(device: torch.device) -> "torch.cuda.Stream":
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    s = _branch_streams.get(idx)
+    if s is None:
+        s = _branch_streams[idx] = torch.cuda.Stream(device=idx)
+    return s
 
 
 class ImageCrossAttentionProcessor(nn.Module):
@@ -170,8 +185,23 @@ class ImageCrossAttentionProcessor(nn.Module):
             else:
                 proj = ops.linear(hs2d, pk["w_in"]).view(b, s, 4 * c)
                 q, k, v, q_ref = (proj[:, :, i * c:(i + 1) * c] for i in range(4))
-            ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])
-            ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:])
+            # The two branches are independent until the fused out-projection. Each launch is a non-integral
+            # number of one-CTA-per-SM waves, so the reference branch is forked onto a second stream to fill the
+            # tail of the first (inside a captured step this becomes two parallel graph branches).
+            if OVERLAP_BRANCHES:
+                main = torch.cuda.current_stream()
+                side = _branch_stream(hidden_states.device)
+                fork, join = torch.cuda.Event(), torch.cuda.Event()
+                fork.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(fork)
+                    ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:])
+                    join.record(side)
+                ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])
+                main.wait_event(join)
+            else:
+                ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])
+                ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:])
             out = ops.linear(cat.view(b * s, 2 * c), pk["w_out"], bias=pk["b_out"], residual=res2d)
             return out.view(b, s, c)
 
