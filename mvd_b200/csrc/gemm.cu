@@ -12,10 +12,10 @@
 // Layout: activations are NHWC bf16 ([rows, C] row-major == K-major A operand), weights are [N, K]
 // row-major bf16 (K-major B operand; for convs K = tap*Cin + c). Accumulation fp32 in TMEM.
 //
-// CTA = 192 threads: warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer, warps 2..5
-// epilogue (TMEM -> registers -> fused bias / per-image bias / residual / GEGLU -> bf16 -> smem -> TMA store).
-// Persistent: grid = min(#tiles, #SMs); two TMEM accumulator stages so the epilogue of tile i overlaps the
-// main loop of tile i+1.
+// CTA = 320 threads: warp 0 TMA producer, warp 1 TMEM owner + single-thread MMA issuer, warps 2..5 and 6..9 two
+// epilogue warpgroups (TMEM -> registers -> fused bias / per-image bias / residual / GEGLU -> bf16 -> smem -> TMA
+// store), one per TMEM accumulator stage. Persistent: grid = min(#tiles, #SMs); the epilogues of tiles i and i+1
+// overlap each other and the main loop of tile i+2's predecessor stage.
 #include "tc.cuh"
 #include "host_common.h"
 #include "../../include/mvd_b200.h"
@@ -26,6 +26,11 @@ constexpr int BM = 128;  // tile rows (output pixels)
 constexpr int BK = 64;   // bf16 elements per k-block = one 128-B swizzle row
 constexpr int EPI_BUFS = 4;
 constexpr int EPI_BUF_BYTES = 32 * 32 * 2;  // 32 rows x 32 bf16
+// Two epilogue warpgroups, one per TMEM accumulator stage (warpgroup w drains the CTA's tiles w, w+2, ...): with a
+// single warpgroup the small-K GEMMs (K = 320 projections, GEGLU) were bound by the epilogue's instruction issue
+// (one warp per scheduler), not by the MMA pipe.
+constexpr int EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 32 * (2 + EPI_WARPS);
 
 struct GemmArgs {
   int tiles_total, tiles_n;
@@ -52,12 +57,13 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int EPI_BYTES = 4 * EPI_BUFS * EPI_BUF_BYTES;  // 32 KB
+  static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;  // 64 KB
   static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
   static constexpr int BAR_BYTES = 1024;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+  static_assert(TOTAL <= 227 * 1024, "shared memory budget of one CTA");
 };
 
 // Exact (erf) GELU, x * Phi(x), as diffusers' GEGLU uses. The GEGLU epilogue is instruction-bound (4 epilogue warps,
@@ -78,7 +84,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 template <int BN, bool S2>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                  const __grid_constant__ CUtensorMap mapRes, const GemmArgs p) {
@@ -91,8 +97,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   uint64_t* empty = bars + L::STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * L::STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint64_t* res_bar = tmem_empty + 2;          // [4 warps][EPI_BUFS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + 4 * EPI_BUFS);
+  uint64_t* res_bar = tmem_empty + 2;          // [EPI_WARPS][EPI_BUFS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS * EPI_BUFS);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
@@ -110,7 +116,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 4);
     }
-    for (int i = 0; i < 4 * EPI_BUFS; ++i) mbar_init(&res_bar[i], 1);
+    for (int i = 0; i < EPI_WARPS * EPI_BUFS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -204,9 +210,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
   } else {
     // ===================== epilogue warps =====================
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    uint8_t* my_smem = epi_smem + q * (EPI_BUFS * EPI_BUF_BYTES);
-    uint64_t* my_res_bar = res_bar + q * EPI_BUFS;
+    const int q = warp & 3;          // TMEM lane quadrant this warp may access
+    const int wg = (warp - 2) >> 2;  // epilogue warpgroup = the accumulator stage it drains
+    uint8_t* my_smem = epi_smem + (wg * 4 + q) * (EPI_BUFS * EPI_BUF_BYTES);
+    uint64_t* my_res_bar = res_bar + (wg * 4 + q) * EPI_BUFS;
     const int r0 = q * 32;  // first tile row of this warp
     // position of this warp's 32-pixel slab inside the tile
     const int wx_off = r0 % p.TW;
@@ -221,8 +228,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int n_out = p.geglu ? p.N / 2 : p.N;
 
     uint32_t g = 0;  // running chunk counter -> staging buffer + barrier parity
-    int it = 0;
-    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+    int it = wg;     // index of the tile in this CTA's sequence: stage it & 1 == wg
+    for (int t = blockIdx.x + wg * gridDim.x; t < p.tiles_total; t += 2 * gridDim.x, it += 2) {
       const int n_tile = t % p.tiles_n;
       int m_tile = t / p.tiles_n;
       const int x0 = (m_tile % p.tiles_x) * p.TW;
@@ -425,7 +432,7 @@ static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUten
     configured = true;
   }
   int grid = args.tiles_total < sm_count() ? args.tiles_total : sm_count();
-  MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, S2>, dim3(grid), dim3(192), L::TOTAL, stream, mA, mA2, mB, mO, mR, args));
+  MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, S2>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, mA, mA2, mB, mO, mR, args));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
