@@ -53,19 +53,32 @@ film_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out
   }
   __syncthreads();
   const int nvec_row = C / 8;
-  const int64_t total = static_cast<int64_t>(hw) * nvec_row;
-  const int64_t per_block = (total + gridDim.x - 1) / gridDim.x;
-  const int64_t i0 = per_block * blockIdx.x;
-  const int64_t i1 = (i0 + per_block < total) ? i0 + per_block : total;
+  const int total = hw * nvec_row;  // 16-byte vectors per image (host checks that this fits in 31 bits)
+  const int per_block = (total + gridDim.x - 1) / gridDim.x;
+  const int i0 = per_block * blockIdx.x;
+  const int i1 = (i0 + per_block < total) ? i0 + per_block : total;
   const __nv_bfloat16* xb = x + static_cast<int64_t>(n) * hw * C;
   __nv_bfloat16* ob = out + static_cast<int64_t>(n) * hw * C;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
-    const int c = static_cast<int>(i % nvec_row) * 8;
-    float f[8];
-    ew_unpack8(*reinterpret_cast<const uint4*>(xb + i * 8), f);
+  constexpr int U = 4;  // independent 16-byte loads in flight per thread
+  for (int i = i0 + threadIdx.x; i < i1; i += U * blockDim.x) {
+    uint4 raw[U];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] = f[k] * s_coef[c + k] + s_coef[C + c + k];
-    *reinterpret_cast<uint4*>(ob + i * 8) = ew_pack8(f);
+    for (int u = 0; u < U; ++u) {
+      const int ii = i + u * blockDim.x;
+      raw[u] = ii < i1 ? *reinterpret_cast<const uint4*>(xb + static_cast<int64_t>(ii) * 8) : make_uint4(0u, 0u, 0u, 0u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int ii = i + u * blockDim.x;
+      if (ii < i1) {
+        const int c = (ii % nvec_row) * 8;
+        float f[8];
+        ew_unpack8(raw[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = f[k] * s_coef[c + k] + s_coef[C + c + k];
+        *reinterpret_cast<uint4*>(ob + static_cast<int64_t>(ii) * 8) = ew_pack8(f);
+      }
+    }
   }
 }
 
@@ -440,9 +453,11 @@ int mvd_film_bf16(const void* x, void* out, const float* mod, int n_img, int n_c
   using namespace mvd;
   MVD_CHECK(n_img > 0 && n_cam > 0 && hw > 0 && channels % 8 == 0 && channels <= 4096, "film: bad shape C=%d",
             channels);
-  int bx = static_cast<int>((static_cast<int64_t>(hw) * channels / 8 + 2047) / 2048);
+  MVD_CHECK(static_cast<int64_t>(hw) * channels / 8 < (1ll << 30), "film: image too large (hw=%d C=%d)", hw, channels);
+  // ~4 batches of 4 vectors per thread; at most ~8 resident blocks per SM over the whole grid
+  int bx = static_cast<int>((static_cast<int64_t>(hw) * channels / 8 + 4095) / 4096);
   if (bx < 1) bx = 1;
-  if (bx > 64) bx = 64;
+  while (bx > 1 && static_cast<int64_t>(bx) * n_img > 1184) bx = (bx + 1) / 2;
   MVD_CUDA(launch_pdl(film_kernel, dim3(bx, n_img), dim3(256), 2 * channels * sizeof(float),
                       static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x),
                       static_cast<__nv_bfloat16*>(out), mod, n_cam, hw, channels, strength));

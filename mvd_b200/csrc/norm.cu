@@ -404,8 +404,11 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
 }
 
 // ------------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, row held in registers, two-pass (exact mean, then centered variance)
+// LayerNorm: one warp per row, row held in registers, two-pass (exact mean, then centered variance). Each warp walks
+// rows with a grid stride and loads its next row before it reduces the current one, so a row's memory round trip
+// overlaps the previous row's arithmetic (one-row-per-warp blocks spent most of their life in launch + first load).
 // ------------------------------------------------------------------------------------------------
+
 template <int VPL>  // 16-byte vectors per lane: C = 32 * 8 * VPL at most
 __global__ void __launch_bounds__(256)
 layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __nv_bfloat16* __restrict__ gamma,
@@ -413,46 +416,65 @@ layernorm_bf16_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const __
                       int C, float eps) {
   pdl_wait();
   pdl_launch_dependents();
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * 8;
+  int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
   const int nvec = C / 8;
-  float f[VPL][8];
-  float s = 0.f;
+  const float inv_c = 1.f / static_cast<float>(C);
+  uint4 raw[VPL];
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
     const int v = lane + i * 32;
-    if (v < nvec) {
-      unpack8(*reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + v * 8), f[i]);
+    raw[i] = v < nvec ? *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * ldx + v * 8)
+                      : make_uint4(0u, 0u, 0u, 0u);
+  }
+  while (true) {
+    const int next = row + stride;
+    uint4 nraw[VPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      nraw[i] = (next < M && v < nvec) ? *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(next) * ldx + v * 8)
+                                       : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float f[VPL][8];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      unpack8(raw[i], f[i]);  // lanes beyond the row hold zeros: they add nothing to the sum
 #pragma unroll
       for (int k = 0; k < 8; ++k) s += f[i][k];
     }
-  }
-  const float mean = warp_sum(s) / C;
-  float q = 0.f;
+    const float mean = warp_sum(s) * inv_c;
+    float q = 0.f;
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
+    for (int i = 0; i < VPL; ++i) {
+      if (lane + i * 32 < nvec) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float d = f[i][k] - mean;
-        q += d * d;
+        for (int k = 0; k < 8; ++k) {
+          const float d = f[i][k] - mean;
+          q += d * d;
+        }
       }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(q) / C + eps);
+    const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      float gm[8], bt[8], o[8];
-      unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
-      unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
+    for (int i = 0; i < VPL; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        float gm[8], bt[8], o[8];
+        unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), gm);
+        unpack8(__ldg(reinterpret_cast<const uint4*>(beta + v * 8)), bt);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) o[k] = (f[i][k] - mean) * rstd * gm[k] + bt[k];
-      *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + v * 8) = pack8(o);
+        for (int k = 0; k < 8; ++k) o[k] = (f[i][k] - mean) * rstd * gm[k] + bt[k];
+        *reinterpret_cast<uint4*>(out + static_cast<int64_t>(row) * ldo + v * 8) = pack8(o);
+      }
     }
+    if (next >= M) break;
+    row = next;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) raw[i] = nraw[i];
   }
 }
 
@@ -681,8 +703,10 @@ int mvd_layernorm_bf16(const void* x, int64_t ldx, const void* gamma, const void
   MVD_CHECK(M > 0 && C > 0 && C % 8 == 0 && C <= 2048 && ldx % 8 == 0 && ldo % 8 == 0,
             "layernorm: C (=%d) must be a multiple of 8 and <= 2048, strides multiples of 8", C);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int blocks = (M + 7) / 8;
   const int vpl = (C / 8 + 31) / 32;
+  int blocks = (M + 7) / 8;
+  const int resident = sm_count() * (vpl <= 2 ? 4 : 2);  // 60 / 107-128 registers per thread
+  if (blocks > resident) blocks = resident;
   auto xx = static_cast<const __nv_bfloat16*>(x);
   auto g = static_cast<const __nv_bfloat16*>(gamma);
   auto b = static_cast<const __nv_bfloat16*>(beta);
