@@ -36,6 +36,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch  # noqa: E402
 
 VIEWS, LATENT, CFG = 4, 64, 2
+WORKLOAD = ("configs[1]: one SD2.1 UNet + MV-adapter denoise step, 4 views at 512^2 (64^2 latent), CFG batch 2")
 GUIDANCE = 3.0
 INFER_STEPS = 50
 FLOPS_PER_STEP = 8.80e12  # 8 samples x 1151.6 GF minus the cached K/V projections
@@ -300,8 +301,7 @@ def run_ours(args):
             "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "configs[1]: one SD2.1 UNet + MV-adapter denoise step, 4 views at 512^2 (64^2 latent), "
-                                   "CFG batch 2, bf16, random-init weights", "views": VIEWS, "cfg": CFG, "latent": LATENT,
+            "config": {"workload": WORKLOAD + ", bf16, random-init weights", "views": VIEWS, "cfg": CFG, "latent": LATENT,
                        "parallelism": plan["desc"], "l2": "working set (1.9 GB weights + activations) >> 126 MB L2; no flush",
                        "cuda_graph": True, "step_invariant_cached": "reference-UNet features, reference/text K/V, camera emb"},
             "clocks": clocks,
@@ -394,8 +394,8 @@ def run_reference(args):
         "unit": "steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": k, "warmup": w,
         "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": "configs[1] (bounded CPU sample, FLOP-scaled)", "views": VIEWS, "cfg": CFG,
-                   "latent": LATENT},
+        "config": {"workload": WORKLOAD + ", fp32 on the host cores, random-init weights; timed on a bounded sample "
+                               "(cpu_baseline.sample) and scaled by FLOPs", "views": VIEWS, "cfg": CFG, "latent": LATENT},
         "cpu_baseline": best,
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
