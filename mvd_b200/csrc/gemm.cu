@@ -52,13 +52,15 @@ struct GemmArgs {
   const float* img_bias;      // [imgs, img_bias_ld] fp32 (e.g. time-embedding projection)
 };
 
-template <int BN>
+template <int BN, int CTAS = 1>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int B_BYTES = (BN / CTAS) * BK * 2;  // a CTA of a pair stages its half of the weight tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;  // 64 KB
-  static constexpr int STAGES = (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
+  static constexpr int STAGES = CTAS == 2 ? ((BN <= 160) ? 6 : 5)
+                                          : (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
+  static_assert(STAGE_BYTES % 1024 == 0, "128B-swizzled tiles must stay 1024-byte aligned");
   static constexpr int BAR_BYTES = 1024;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
@@ -83,12 +85,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 
-template <int BN, bool S2>
+template <int BN, bool S2, int CTAS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                  const __grid_constant__ CUtensorMap mapRes, const GemmArgs p) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CTAS>;
+  // CTAS == 2: the grid is made of 2-CTA clusters; a pair computes a 256 x BN tile with cta_group::2 MMAs issued by
+  // its even-ranked (leader) CTA. Every CTA loads its own 128 rows of A and its half of the weight tile, drains its
+  // own 128 accumulator lanes and stores its own rows; only the barriers the MMA waits on live in the leader.
+  constexpr bool PAIR = CTAS == 2;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit = blockIdx.x / CTAS;  // scheduling unit (CTA or CTA pair) and their number
+  const int n_units = gridDim.x / CTAS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_smem = smem + L::STAGES * L::STAGE_BYTES;
@@ -114,17 +124,27 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], 4 * CTAS);  // the epilogue warps of every CTA of the pair
     }
     for (int i = 0; i < EPI_WARPS * EPI_BUFS; ++i) mbar_init(&res_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, L::TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, L::TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, L::TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) {  // the peer's barriers must be initialised before anything is signalled on them
+    cluster_arrive();
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; from here on we read its results
@@ -135,9 +155,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+      const uint32_t lead_full = PAIR ? mapa_shared(smem_u32(&full[0]), 0) : 0u;  // leader's full[] barriers
+      for (int t = unit; t < p.tiles_total; t += n_units) {
         const int n_tile = t % p.tiles_n;
-        int m_tile = t / p.tiles_n;
+        int m_tile = (t / p.tiles_n) * CTAS + static_cast<int>(rank);
         const int x0 = (m_tile % p.tiles_x) * p.TW;
         m_tile /= p.tiles_x;
         const int y0 = (m_tile % p.tiles_y) * p.TH;
@@ -149,19 +170,37 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + L::A_BYTES;
-            mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
-            if constexpr (S2) {
-              // input pixel (2*oy + ky - 1, 2*ox + kx - 1) in the [N, H/2, 2, W/2, 2C] view
-              const int px = (kx == 1) ? 0 : 1, py = (ky == 1) ? 0 : 1;
-              const int wx = x0 + ((kx == 0) ? -1 : 0), hy = y0 + ((ky == 0) ? -1 : 0);
-              tma_load_5d(sa, &mapA, &full[stage], px * p.c_s2 + kc * BK, wx, py, hy, n0);
+            if constexpr (PAIR) {
+              // both CTAs' bytes are counted on the leader's barrier (the peer's stage was released by the same
+              // multicast commit as the leader's, so it cannot run a whole phase ahead of the leader's expect_tx)
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
+              const uint32_t fb = lead_full + stage * 8;
+              if constexpr (S2) {
+                const int px = (kx == 1) ? 0 : 1, py = (ky == 1) ? 0 : 1;
+                const int wx = x0 + ((kx == 0) ? -1 : 0), hy = y0 + ((ky == 0) ? -1 : 0);
+                tma_load_5d_pair(sa, &mapA, fb, px * p.c_s2 + kc * BK, wx, py, hy, n0);
+              } else {
+                if (kc < p.kc_a1)
+                  tma_load_4d_pair(sa, &mapA, fb, kc * BK, x0 + kx - 1, y0 + ky - 1, n0);
+                else
+                  tma_load_4d_pair(sa, &mapA2, fb, (kc - p.kc_a1) * BK, x0 + kx - 1, y0 + ky - 1, n0);
+              }
+              tma_load_2d_pair(sb, &mapB, fb, tap * p.cin + kc * BK, n_tile * BN + static_cast<int>(rank) * (BN / 2));
             } else {
-              if (kc < p.kc_a1)
-                tma_load_4d(sa, &mapA, &full[stage], kc * BK, x0 + kx - 1, y0 + ky - 1, n0);
-              else
-                tma_load_4d(sa, &mapA2, &full[stage], (kc - p.kc_a1) * BK, x0 + kx - 1, y0 + ky - 1, n0);
+              mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+              if constexpr (S2) {
+                // input pixel (2*oy + ky - 1, 2*ox + kx - 1) in the [N, H/2, 2, W/2, 2C] view
+                const int px = (kx == 1) ? 0 : 1, py = (ky == 1) ? 0 : 1;
+                const int wx = x0 + ((kx == 0) ? -1 : 0), hy = y0 + ((ky == 0) ? -1 : 0);
+                tma_load_5d(sa, &mapA, &full[stage], px * p.c_s2 + kc * BK, wx, py, hy, n0);
+              } else {
+                if (kc < p.kc_a1)
+                  tma_load_4d(sa, &mapA, &full[stage], kc * BK, x0 + kx - 1, y0 + ky - 1, n0);
+                else
+                  tma_load_4d(sa, &mapA2, &full[stage], (kc - p.kc_a1) * BK, x0 + kx - 1, y0 + ky - 1, n0);
+              }
+              tma_load_2d(sb, &mapB, &full[stage], tap * p.cin + kc * BK, n_tile * BN);
             }
-            tma_load_2d(sb, &mapB, &full[stage], tap * p.cin + kc * BK, n_tile * BN);
             if (++stage == L::STAGES) {
               stage = 0;
               phase ^= 1;
@@ -170,17 +209,17 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (of a pair: the leader CTA only) =====================
     // Warp-uniform control flow: all lanes wait on the barriers and build the descriptors (uniform registers),
     // one elected lane issues the tcgen05.mma / commit instructions.
-    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++it) {
+    for (int t = unit; t < p.tiles_total; t += n_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -194,10 +233,17 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
         if (elect_one()) {
           // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
-          umma_ss(d_tmem, adesc, bdesc, idesc, kb != 0);
+          if constexpr (PAIR) {
+            umma_ss_pair(d_tmem, adesc, bdesc, idesc, kb != 0);
 #pragma unroll
-          for (int k = 1; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
-          umma_commit(&empty[stage]);
+            for (int k = 1; k < BK / 16; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            umma_commit_pair(&empty[stage], 3);  // frees the stage in both CTAs
+          } else {
+            umma_ss(d_tmem, adesc, bdesc, idesc, kb != 0);
+#pragma unroll
+            for (int k = 1; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+            umma_commit(&empty[stage]);
+          }
         }
         __syncwarp();
         if (++stage == L::STAGES) {
@@ -205,10 +251,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           phase ^= 1;
         }
       }
-      if (elect_one()) umma_commit(&tmem_full[acc]);
+      if (elect_one()) {
+        if constexpr (PAIR)
+          umma_commit_pair(&tmem_full[acc], 3);  // both CTAs' epilogues drain their half of the accumulator
+        else
+          umma_commit(&tmem_full[acc]);
+      }
       __syncwarp();
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue warps =====================
     const int q = warp & 3;          // TMEM lane quadrant this warp may access
     const int wg = (warp - 2) >> 2;  // epilogue warpgroup = the accumulator stage it drains
@@ -229,9 +280,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     uint32_t g = 0;  // running chunk counter -> staging buffer + barrier parity
     int it = wg;     // index of the tile in this CTA's sequence: stage it & 1 == wg
-    for (int t = blockIdx.x + wg * gridDim.x; t < p.tiles_total; t += 2 * gridDim.x, it += 2) {
+    const uint32_t lead_tmem_empty = PAIR ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
+    for (int t = unit + wg * n_units; t < p.tiles_total; t += 2 * n_units, it += 2) {
       const int n_tile = t % p.tiles_n;
-      int m_tile = t / p.tiles_n;
+      int m_tile = (t / p.tiles_n) * CTAS + static_cast<int>(rank);
       const int x0 = (m_tile % p.tiles_x) * p.TW;
       m_tile /= p.tiles_x;
       const int y0 = (m_tile % p.tiles_y) * p.TH;
@@ -377,17 +429,30 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       // accumulator fully read -> hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (PAIR && !leader)
+          mbar_arrive_cluster(lead_tmem_empty + acc * 8);  // the MMA issuer waits on the leader's barrier
+        else
+          mbar_arrive(&tmem_empty[acc]);
+      }
     }
     if (lane == 0) tma_store_wait_all0();
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (PAIR) {  // no CTA may exit (or free TMEM) while its peer's MMAs / remote arrivals are in flight
+    cluster_arrive();
+    cluster_wait();
+  } else {
+    __syncthreads();
+  }
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem_base, L::TMEM_COLS);
+    if constexpr (PAIR)
+      tmem_dealloc_pair(tmem_base, L::TMEM_COLS);
+    else
+      tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -422,20 +487,64 @@ static void pick_tile(int Nimg, int H, int W, int* TW, int* TH, int* TN) {
   (void)Nimg;
 }
 
-template <int BN, bool S2>
+// CTA-pair (cta_group::2) tiles: EXPERIMENTAL, off unless MVD_GEMM_2CTA=1 — written against the L2<->SM traffic
+// ceiling measured in profiles/r1_tma_bw.txt, not yet run on hardware.
+static bool pair_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MVD_GEMM_2CTA");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
+template <int BN, bool S2, int CTAS>
 static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
                       const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, CTAS>;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
-    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, S2, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  L::TOTAL));
     configured = true;
   }
-  int grid = args.tiles_total < sm_count() ? args.tiles_total : sm_count();
-  MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, S2>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, mA, mA2, mB, mO, mR, args));
+  int units = sm_count() / CTAS;  // CTAs, or CTA pairs (one CTA per SM)
+  if (args.tiles_total < units) units = args.tiles_total;
+  if constexpr (CTAS == 1) {
+    MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, S2, 1>, dim3(units), dim3(GEMM_THREADS), L::TOTAL, stream, mA, mA2, mB,
+                        mO, mR, args));
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(units * CTAS);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = L::TOTAL;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CTAS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    int na = 1;
+    if (pdl_enabled()) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    MVD_CUDA(cudaLaunchKernelEx(&cfg, gemm_conv_kernel<BN, S2, CTAS>, mA, mA2, mB, mO, mR, args));
+  }
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
+}
+
+static double bn_cost(int N, int M_tiles, int bn, int units) {
+  const int tn = (N + bn - 1) / bn;
+  const long tiles = static_cast<long>(tn) * M_tiles;
+  const long waves = (tiles + units - 1) / units;
+  // cost ~ waves * per-tile time (prop. to bn) ; small fixed per-tile overhead favours larger tiles
+  return static_cast<double>(waves) * (bn + 24.0);
 }
 
 static int pick_bn(int N, int M_tiles, bool geglu) {
@@ -444,22 +553,29 @@ static int pick_bn(int N, int M_tiles, bool geglu) {
   const int cands_geglu[] = {256, 128, 64};
   const int* cands = geglu ? cands_geglu : cands_plain;
   const int nc = geglu ? 3 : 4;
-  const int sms = sm_count();
   int best = 64;
   double best_cost = 1e30;
   for (int i = 0; i < nc; ++i) {
-    const int bn = cands[i];
-    const int tn = (N + bn - 1) / bn;
-    const long tiles = static_cast<long>(tn) * M_tiles;
-    const long waves = (tiles + sms - 1) / sms;
-    // cost ~ waves * per-tile time (prop. to bn) ; small fixed per-tile overhead favours larger tiles
-    const double cost = static_cast<double>(waves) * (bn + 24.0);
+    const double cost = bn_cost(N, M_tiles, cands[i], sm_count());
     if (cost < best_cost) {
       best_cost = cost;
-      best = bn;
+      best = cands[i];
     }
   }
   return best;
+}
+
+// Tile width of a CTA-pair launch (256 x BN tiles over sm_count()/2 pairs), or 0 when pairs are off / not worthwhile:
+// a pair tile costs about what a single-CTA tile of the same width costs, so the two cost figures compare directly.
+static int pick_bn_pair(int N, int M_tiles, int force_bn, int single_bn) {
+  if (!pair_enabled() || M_tiles < 2) return 0;
+  const int m_pairs = (M_tiles + 1) / 2;
+  const int units = sm_count() / 2;
+  if (force_bn > 0) return (force_bn == 256 || force_bn == 160) ? force_bn : 0;
+  const double c160 = bn_cost(N, m_pairs, 160, units), c256 = bn_cost(N, m_pairs, 256, units);
+  const int bn = c256 <= c160 ? 256 : 160;
+  const double single = bn_cost(N, M_tiles, single_bn, sm_count());
+  return (c256 <= c160 ? c256 : c160) <= 1.15 * single ? bn : 0;  // operand traffic per FLOP is ~1.6x lower
 }
 
 // Generic launcher. x: NHWC-like activation described as (C, Wd, Hd, Nd) with element strides.
@@ -515,9 +631,12 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   g.img_max = rows_per_img > 0 ? (W - 1) / rows_per_img : Nimg - 1;
   g.bias = static_cast<const __nv_bfloat16*>(bias);
 
-  const int BN = force_bn > 0 ? force_bn : pick_bn(Cout, tiles_m, geglu != 0);
+  int BN = force_bn > 0 ? force_bn : pick_bn(Cout, tiles_m, geglu != 0);
+  const int pair_bn = pick_bn_pair(Cout, tiles_m, force_bn, BN);
+  const int ctas = pair_bn > 0 ? 2 : 1;
+  if (pair_bn > 0) BN = pair_bn;
   g.tiles_n = (Cout + BN - 1) / BN;
-  g.tiles_total = g.tiles_n * tiles_m;
+  g.tiles_total = g.tiles_n * ((tiles_m + ctas - 1) / ctas);  // scheduling units: tiles, or 256-row pair tiles
 
   CUtensorMap mA, mA2, mB, mO, mR;
   // --- A maps
@@ -554,7 +673,7 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(ntaps) * Cin, static_cast<uint64_t>(Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(BN / ctas)};  // a CTA of a pair loads its half of the tile
     if (int e = make_tmap_bf16(&mB, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
   // --- output / residual maps (per-warp slab boxes of 32 pixels x 32 channels, 64-B swizzle)
@@ -580,10 +699,17 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
     }
   }
 
+  if (ctas == 2) {
+    if (BN == 256)
+      return stride == 2 ? launch_one<256, true, 2>(mA, mA2, mB, mO, mR, g, stream)
+                         : launch_one<256, false, 2>(mA, mA2, mB, mO, mR, g, stream);
+    return stride == 2 ? launch_one<160, true, 2>(mA, mA2, mB, mO, mR, g, stream)
+                       : launch_one<160, false, 2>(mA, mA2, mB, mO, mR, g, stream);
+  }
 #define MVD_LAUNCH_BN(bn)                                                               \
   case bn:                                                                              \
-    return stride == 2 ? launch_one<bn, true>(mA, mA2, mB, mO, mR, g, stream)           \
-                       : launch_one<bn, false>(mA, mA2, mB, mO, mR, g, stream);
+    return stride == 2 ? launch_one<bn, true, 1>(mA, mA2, mB, mO, mR, g, stream)        \
+                       : launch_one<bn, false, 1>(mA, mA2, mB, mO, mR, g, stream);
   switch (BN) {
     MVD_LAUNCH_BN(64)
     MVD_LAUNCH_BN(128)
