@@ -50,6 +50,10 @@ struct GemmArgs {
   int img_max;           // clamp for the img index (padded rows of the last tile)
   const __nv_bfloat16* bias;  // [N] (permuted like the weight rows when geglu)
   const float* img_bias;      // [imgs, img_bias_ld] fp32 (e.g. time-embedding projection)
+  // split-K (SPLIT kernels only): tiles_total counts (tile, k-slice) work items, slice fastest
+  int splits;                 // k-slices per output tile
+  float* ws_partial;          // [tiles][splits][128][BN] fp32 partial accumulators
+  unsigned int* ws_tickets;   // [tiles][4] arrival counters, one per 32-row warp slab; zero between launches
 };
 
 template <int BN, int CTAS = 1>
@@ -85,7 +89,11 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 
-template <int BN, bool S2, int CTAS>
+// SPLIT: split-K for problems with fewer output tiles than SMs (the 8x8-latent level: M = 512 rows). Each work
+// item is a (tile, k-slice); every CTA writes its fp32 partial rows to a workspace, and per 32-row slab the LAST
+// arriving warp (ticket counter, re-armed for the next launch) adds the slices in slice order — deterministic —
+// and runs the normal epilogue on the sum.
+template <int BN, bool S2, int CTAS, bool SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
@@ -157,8 +165,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       uint32_t phase = 0;
       const uint32_t lead_full = PAIR ? mapa_shared(smem_u32(&full[0]), 0) : 0u;  // leader's full[] barriers
       for (int t = unit; t < p.tiles_total; t += n_units) {
-        const int n_tile = t % p.tiles_n;
-        int m_tile = (t / p.tiles_n) * CTAS + static_cast<int>(rank);
+        const int tile = SPLIT ? t / p.splits : t;
+        const int ks = SPLIT ? t - tile * p.splits : 0;
+        [[maybe_unused]] const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
+        [[maybe_unused]] const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
+        [[maybe_unused]] int kb = 0;
+        const int n_tile = tile % p.tiles_n;
+        int m_tile = (tile / p.tiles_n) * CTAS + static_cast<int>(rank);
         const int x0 = (m_tile % p.tiles_x) * p.TW;
         m_tile /= p.tiles_x;
         const int y0 = (m_tile % p.tiles_y) * p.TH;
@@ -167,6 +180,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int ky = (p.ntaps == 9) ? tap / 3 : 1;
           const int kx = (p.ntaps == 9) ? tap % 3 : 1;
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            if constexpr (SPLIT) {  // only the k-blocks of this work item's slice
+              const int cur = kb++;
+              if (cur < kb0 || cur >= kb1) continue;
+            }
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + L::A_BYTES;
@@ -225,7 +242,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tb + acc * L::ACC_STRIDE;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int ks = SPLIT ? t % p.splits : 0;
+      const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
+      const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
@@ -234,12 +254,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         if (elect_one()) {
           // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
           if constexpr (PAIR) {
-            umma_ss_pair(d_tmem, adesc, bdesc, idesc, kb != 0);
+            umma_ss_pair(d_tmem, adesc, bdesc, idesc, kb != kb0);
 #pragma unroll
             for (int k = 1; k < BK / 16; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
             umma_commit_pair(&empty[stage], 3);  // frees the stage in both CTAs
           } else {
-            umma_ss(d_tmem, adesc, bdesc, idesc, kb != 0);
+            umma_ss(d_tmem, adesc, bdesc, idesc, kb != kb0);
 #pragma unroll
             for (int k = 1; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
             umma_commit(&empty[stage]);
@@ -282,8 +302,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int it = wg;     // index of the tile in this CTA's sequence: stage it & 1 == wg
     const uint32_t lead_tmem_empty = PAIR ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
     for (int t = unit + wg * n_units; t < p.tiles_total; t += 2 * n_units, it += 2) {
-      const int n_tile = t % p.tiles_n;
-      int m_tile = (t / p.tiles_n) * CTAS + static_cast<int>(rank);
+      const int tile = SPLIT ? t / p.splits : t;
+      const int n_tile = tile % p.tiles_n;
+      int m_tile = (tile / p.tiles_n) * CTAS + static_cast<int>(rank);
       const int x0 = (m_tile % p.tiles_x) * p.TW;
       m_tile /= p.tiles_x;
       const int y0 = (m_tile % p.tiles_y) * p.TH;
@@ -292,6 +313,39 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int col_base = n_tile * out_cols_per_tile;
+
+      [[maybe_unused]] const float* part_rd = nullptr;
+      if constexpr (SPLIT) {
+        // publish this k-slice's fp32 partial rows, hand the accumulator back, take a ticket for the 32-row slab
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_part = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+        const int ks = t - tile * p.splits;
+        float* part = p.ws_partial + (static_cast<size_t>(tile) * p.splits + ks) * (BM * BN) +
+                      static_cast<size_t>(row) * BN;
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_part + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(part + c * 32 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        }
+        tc_fence_before();
+        __threadfence();  // partial rows visible device-wide before the ticket is taken
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          mbar_arrive(&tmem_empty[acc]);
+          unsigned int* tk = p.ws_tickets + tile * 4 + q;
+          last = atomicAdd(tk, 1u) == static_cast<unsigned int>(p.splits - 1);
+          if (last) *tk = 0u;  // re-arm for the next launch
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        __threadfence();
+        part_rd = p.ws_partial + static_cast<size_t>(tile) * p.splits * (BM * BN) + static_cast<size_t>(row) * BN;
+      }
 
       // prefetch residual slabs for the first two chunks (their buffers are free: at most one store
       // group from the previous tile may still be reading, and it is neither of these two buffers
@@ -308,8 +362,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
       }
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      if constexpr (!SPLIT) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+      }
       const uint32_t t_acc = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
       int img = ln + n0 + (x0 + lx) / p.rows_per_img;
       img = img < p.img_max ? img : p.img_max;
@@ -338,11 +394,25 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         float v[32];
         if (!p.geglu) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_acc + c * 32, r);
-          tmem_ld_wait();
+          if constexpr (SPLIT) {
+            // slices in slice order (fixed summation order whichever CTA arrived last); L2-coherent loads
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int sl = 0; sl < p.splits; ++sl) {
+              const float4* src = reinterpret_cast<const float4*>(part_rd + static_cast<size_t>(sl) * (BM * BN) + c * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 f = __ldcg(src + j);
+                v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+              }
+            }
+          } else {
+            uint32_t r[32];
+            tmem_ld_32x32b_x32(t_acc + c * 32, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          }
           if (col0 + 32 <= p.N) {  // N is a multiple of 32: a chunk is either fully inside or fully outside
             if (p.bias != nullptr) {
               const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);  // 64-byte aligned
@@ -426,10 +496,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_store_commit();
         }
       }
-      // accumulator fully read -> hand the TMEM stage back to the MMA warp
+      // accumulator fully read -> hand the TMEM stage back to the MMA warp (SPLIT: already done above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) {
+      if (!SPLIT && lane == 0) {
         if (PAIR && !leader)
           mbar_arrive_cluster(lead_tmem_empty + acc * 8);  // the MMA issuer waits on the leader's barrier
         else
@@ -497,6 +567,52 @@ static bool pair_enabled() {
   return on;
 }
 
+// Split-K: EXPERIMENTAL, off unless MVD_GEMM_SPLITK=1 and the caller registered a workspace
+// (mvd_gemm_set_workspace) — not yet run on hardware.
+static bool splitk_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MVD_GEMM_SPLITK");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+static thread_local void* t_gemm_ws = nullptr;  // caller-owned, zero-filled once; see mvd_gemm_set_workspace
+static thread_local int64_t t_gemm_ws_bytes = 0;
+constexpr int64_t SPLITK_TICKET_BYTES = 4096 * sizeof(unsigned int);
+
+// Cost of one CTA's work in 128-byte rows moved between L2 and the SM (the measured bound of these kernels):
+// operand rows of its k-slice + the fp32 fix-up traffic of the last arriver (write 4*bn rows, read splits * 4*bn).
+static double splitk_cost(int bn, int k_blocks, int splits) {
+  const int kb = (k_blocks + splits - 1) / splits;
+  return static_cast<double>(128 + bn) * kb + (splits > 1 ? 4.0 * bn * (splits + 1) : 0.0);
+}
+
+// Picks (bn, splits) for an under-filled launch, or splits = 1. tiles_m: 128-row tiles.
+static void pick_splitk(int N, int tiles_m, int k_blocks, int single_bn, int* bn_out, int* splits_out) {
+  *bn_out = single_bn;
+  *splits_out = 1;
+  const int sms = sm_count();
+  const long tiles1 = static_cast<long>((N + single_bn - 1) / single_bn) * tiles_m;
+  if (!splitk_enabled() || t_gemm_ws == nullptr || tiles1 > sms) return;  // more than one wave: leave it alone
+  double best = splitk_cost(single_bn, k_blocks, 1) * 0.8;  // a split must promise >= 20 %
+  const int cands[] = {160, 128, 64};
+  for (int bn : cands) {
+    const long tiles = static_cast<long>((N + bn - 1) / bn) * tiles_m;
+    if (tiles > 1024) continue;  // ticket table: 4 counters per tile
+    for (int sp = 2; sp <= 8; ++sp) {
+      if (tiles * sp > sms || k_blocks / sp < 4) break;
+      const int64_t need = SPLITK_TICKET_BYTES + static_cast<int64_t>(tiles) * sp * BM * bn * 4;
+      if (need > t_gemm_ws_bytes) break;
+      const double c = splitk_cost(bn, k_blocks, sp);
+      if (c < best) {
+        best = c;
+        *bn_out = bn;
+        *splits_out = sp;
+      }
+    }
+  }
+}
+
 template <int BN, bool S2, int CTAS>
 static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
                       const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
@@ -534,6 +650,24 @@ static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUten
     cfg.numAttrs = na;
     MVD_CUDA(cudaLaunchKernelEx(&cfg, gemm_conv_kernel<BN, S2, CTAS>, mA, mA2, mB, mO, mR, args));
   }
+  MVD_CUDA(cudaGetLastError());
+  count_launches(1);
+  return MVD_OK;
+}
+
+template <int BN>
+static int launch_split(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
+                        const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
+  using L = SmemLayout<BN, 1>;
+  static bool configured = false;
+  if (!configured) {
+    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  L::TOTAL));
+    configured = true;
+  }
+  const int grid = args.tiles_total < sm_count() ? args.tiles_total : sm_count();
+  MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, false, 1, true>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, mA, mA2,
+                      mB, mO, mR, args));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -635,8 +769,20 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   const int pair_bn = pick_bn_pair(Cout, tiles_m, force_bn, BN);
   const int ctas = pair_bn > 0 ? 2 : 1;
   if (pair_bn > 0) BN = pair_bn;
+  int splits = 1;
+  if (ctas == 1 && force_bn == 0 && !geglu && stride == 1) {
+    int bn_split = BN;
+    pick_splitk(Cout, tiles_m, g.ntaps * g.kc_per_tap, BN, &bn_split, &splits);
+    if (splits > 1) BN = bn_split;
+  }
   g.tiles_n = (Cout + BN - 1) / BN;
   g.tiles_total = g.tiles_n * ((tiles_m + ctas - 1) / ctas);  // scheduling units: tiles, or 256-row pair tiles
+  g.splits = splits;
+  if (splits > 1) {
+    g.ws_tickets = static_cast<unsigned int*>(t_gemm_ws);
+    g.ws_partial = reinterpret_cast<float*>(static_cast<char*>(t_gemm_ws) + SPLITK_TICKET_BYTES);
+    g.tiles_total *= splits;  // work items: (tile, k-slice), slice fastest
+  }
 
   CUtensorMap mA, mA2, mB, mO, mR;
   // --- A maps
@@ -699,6 +845,13 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
     }
   }
 
+  if (splits > 1) {
+    switch (BN) {
+      case 64: return launch_split<64>(mA, mA2, mB, mO, mR, g, stream);
+      case 128: return launch_split<128>(mA, mA2, mB, mO, mR, g, stream);
+      default: return launch_split<160>(mA, mA2, mB, mO, mR, g, stream);
+    }
+  }
   if (ctas == 2) {
     if (BN == 256)
       return stride == 2 ? launch_one<256, true, 2>(mA, mA2, mB, mO, mR, g, stream)
@@ -725,6 +878,16 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
 }  // namespace mvd
 
 extern "C" {
+
+int mvd_gemm_set_workspace(void* workspace, int64_t bytes) {
+  using namespace mvd;
+  MVD_CHECK(workspace == nullptr || ((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && bytes > SPLITK_TICKET_BYTES),
+            "gemm workspace must be 16-byte aligned and larger than %lld bytes",
+            static_cast<long long>(SPLITK_TICKET_BYTES));
+  t_gemm_ws = workspace;
+  t_gemm_ws_bytes = workspace ? bytes : 0;
+  return MVD_OK;
+}
 
 int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
                     int64_t ldw, const void* bias, const float* row_group_bias, int row_group_bias_ld,

@@ -26,7 +26,8 @@ def _randn(*shape, scale=1.0, seed=0):
 
 
 @pytest.mark.parametrize("tile_n", [0, 64, 128, 160, 256])
-@pytest.mark.parametrize("M,N,K", [(1000, 320, 320), (256, 1280, 640), (77, 640, 1024), (4096, 320, 1280)])
+@pytest.mark.parametrize("M,N,K", [(1000, 320, 320), (256, 1280, 640), (77, 640, 1024), (4096, 320, 1280),
+                                   (640, 640, 320), (512, 1280, 5120)])
 def test_linear_plain(M, N, K, tile_n):
     from mvd_b200 import ops
 
