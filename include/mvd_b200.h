@@ -66,6 +66,12 @@ int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const vo
  * the split-K path is experimental) every GEMM runs un-split. No reference analogue (scheduling detail). */
 int mvd_gemm_set_workspace(void* workspace, int64_t bytes);
 
+/* The scheduling decision mvd_linear_bf16 (n_img = h_out = 1, w_out = M, ntaps = 1) / mvd_conv3x3_bf16 (ntaps = 9)
+ * would take for a problem, without launching anything: tile width, CTAs per tile (2 = cta_group::2 pair), k-slices
+ * and grid size. Any output pointer may be NULL. For tests and tuning; no reference analogue. */
+int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntaps, int stride, int geglu, int tile_n,
+                  int* bn, int* ctas, int* splits, int* grid);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Fused flash-attention forward, head_dim 64 (tcgen05 + TMEM + TMA), csrc/attn.cu
  * ------------------------------------------------------------------------------------------------------- */

@@ -712,6 +712,28 @@ static int pick_bn_pair(int N, int M_tiles, int force_bn, int single_bn) {
   return (c256 <= c160 ? c256 : c160) <= 1.15 * single ? bn : 0;  // operand traffic per FLOP is ~1.6x lower
 }
 
+// The scheduling decision for one problem: tile width, CTAs per tile (2 = CTA pair), k-slices.
+struct GemmPlan {
+  int TW, TH, TN, tiles_m;
+  int bn, ctas, splits;
+};
+static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, int stride, int geglu, int force_bn) {
+  GemmPlan pl;
+  pick_tile(Nimg, H, W, &pl.TW, &pl.TH, &pl.TN);
+  pl.tiles_m = ((W + pl.TW - 1) / pl.TW) * ((H + pl.TH - 1) / pl.TH) * ((Nimg + pl.TN - 1) / pl.TN);
+  pl.bn = force_bn > 0 ? force_bn : pick_bn(Cout, pl.tiles_m, geglu != 0);
+  const int pair_bn = pick_bn_pair(Cout, pl.tiles_m, force_bn, pl.bn);
+  pl.ctas = pair_bn > 0 ? 2 : 1;
+  if (pair_bn > 0) pl.bn = pair_bn;
+  pl.splits = 1;
+  if (pl.ctas == 1 && force_bn == 0 && !geglu && stride == 1) {
+    int bn_split = pl.bn;
+    pick_splitk(Cout, pl.tiles_m, ntaps * (Cin / 64), pl.bn, &bn_split, &pl.splits);
+    if (pl.splits > 1) pl.bn = bn_split;
+  }
+  return pl;
+}
+
 // Generic launcher. x: NHWC-like activation described as (C, Wd, Hd, Nd) with element strides.
 struct OperandA {
   const void* ptr;
@@ -741,8 +763,8 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  int TW, TH, TN;
-  pick_tile(Nimg, H, W, &TW, &TH, &TN);
+  const GemmPlan pl = plan_gemm(Nimg, H, W, Cin, Cout, ntaps, stride, geglu, force_bn);
+  const int TW = pl.TW, TH = pl.TH, TN = pl.TN;
   g.TW = TW; g.TH = TH; g.TN = TN;
   g.tiles_x = (W + TW - 1) / TW;
   g.tiles_y = (H + TH - 1) / TH;
@@ -765,16 +787,7 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   g.img_max = rows_per_img > 0 ? (W - 1) / rows_per_img : Nimg - 1;
   g.bias = static_cast<const __nv_bfloat16*>(bias);
 
-  int BN = force_bn > 0 ? force_bn : pick_bn(Cout, tiles_m, geglu != 0);
-  const int pair_bn = pick_bn_pair(Cout, tiles_m, force_bn, BN);
-  const int ctas = pair_bn > 0 ? 2 : 1;
-  if (pair_bn > 0) BN = pair_bn;
-  int splits = 1;
-  if (ctas == 1 && force_bn == 0 && !geglu && stride == 1) {
-    int bn_split = BN;
-    pick_splitk(Cout, tiles_m, g.ntaps * g.kc_per_tap, BN, &bn_split, &splits);
-    if (splits > 1) BN = bn_split;
-  }
+  const int BN = pl.bn, ctas = pl.ctas, splits = pl.splits;
   g.tiles_n = (Cout + BN - 1) / BN;
   g.tiles_total = g.tiles_n * ((tiles_m + ctas - 1) / ctas);  // scheduling units: tiles, or 256-row pair tiles
   g.splits = splits;
@@ -878,6 +891,22 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
 }  // namespace mvd
 
 extern "C" {
+
+int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntaps, int stride, int geglu, int tile_n,
+                  int* bn, int* ctas, int* splits, int* grid) {
+  using namespace mvd;
+  MVD_CHECK(n_img > 0 && h_out > 0 && w_out > 0 && c_in > 0 && c_in % 64 == 0 && c_out > 0 && c_out % 32 == 0 &&
+                (ntaps == 1 || ntaps == 9) && (stride == 1 || stride == 2),
+            "gemm_plan: unsupported problem");
+  const GemmPlan pl = plan_gemm(n_img, h_out, w_out, c_in, c_out, ntaps, stride, geglu, tile_n);
+  const int units = ((c_out + pl.bn - 1) / pl.bn) * ((pl.tiles_m + pl.ctas - 1) / pl.ctas) * pl.splits;
+  const int cap = sm_count() / pl.ctas;
+  if (bn) *bn = pl.bn;
+  if (ctas) *ctas = pl.ctas;
+  if (splits) *splits = pl.splits;
+  if (grid) *grid = (units < cap ? units : cap) * pl.ctas;
+  return MVD_OK;
+}
 
 int mvd_gemm_set_workspace(void* workspace, int64_t bytes) {
   using namespace mvd;

@@ -80,3 +80,53 @@ def test_cpu_forward_is_refused():
     m = mvd_b200.MultiViewUNet(tiny_config(), dtype=torch.float32, use_image_conditioning=False)
     with pytest.raises(RuntimeError, match="CUDA"):
         m(torch.zeros(1, 4, 16, 16), 1, torch.zeros(1, 77, 64))
+
+
+# ---- GEMM scheduling decisions (csrc/gemm.cu: plan_gemm; no GPU needed, the SM count falls back to 148) -------------
+_PLAN_SNIPPET = r"""
+import ctypes, json
+from mvd_b200._lib import lib
+L = lib()
+def plan(n, h, w, cin, cout, taps=1, stride=1, geglu=0, tile=0):
+    o = [ctypes.c_int() for _ in range(4)]
+    assert L.mvd_gemm_plan(n, h, w, cin, cout, taps, stride, geglu, tile, *[ctypes.byref(x) for x in o]) == 0
+    return [x.value for x in o]
+assert L.mvd_gemm_set_workspace(ctypes.c_void_p(0x10000), 16 << 20) == 0   # planning only: never dereferenced
+print(json.dumps({
+    "qkv64": plan(1, 1, 32768, 320, 1280), "proj64": plan(1, 1, 32768, 320, 320),
+    "geglu64": plan(1, 1, 32768, 320, 2560, geglu=1, tile=256), "conv64": plan(8, 64, 64, 320, 320, 9),
+    "conv8": plan(8, 8, 8, 1280, 1280, 9), "ff2_8": plan(1, 1, 512, 5120, 1280), "down8": plan(8, 8, 8, 1280, 1280, 9, 2)}))
+"""
+
+
+def _plans(env_extra):
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if not k.startswith("MVD_GEMM_")}
+    env.update(env_extra, PYTHONPATH=root)
+    out = subprocess.run([sys.executable, "-c", _PLAN_SNIPPET], env=env, capture_output=True, text=True, check=True)
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def test_gemm_plan_default_is_single_cta_unsplit():
+    """[bn, ctas, splits, grid]: by default no launch uses CTA pairs or split-K (both are opt-in, unmeasured)."""
+    p = _plans({})
+    assert all(v[1] == 1 and v[2] == 1 for v in p.values()), p
+    assert p["proj64"][0] == 160 and p["conv64"][0] == 160 and p["conv64"][3] == 148
+    assert p["geglu64"][0] == 256                     # GEGLU tile width is dictated by the weight interleave
+    assert p["conv8"] == [64, 1, 1, 80]               # 4 row tiles x 20 column tiles: the under-filled case
+
+
+def test_gemm_plan_pair_and_splitk_flags():
+    pair = _plans({"MVD_GEMM_2CTA": "1"})
+    assert pair["qkv64"][:3] == [256, 2, 1] and pair["conv64"][:3] == [160, 2, 1]
+    assert pair["conv64"][3] % 2 == 0 and pair["conv64"][3] <= 148
+    assert pair["conv8"][1] == 1                      # 4 row tiles: pairs would only halve the parallelism
+    split = _plans({"MVD_GEMM_SPLITK": "1"})
+    assert split["conv8"][1] == 1 and split["conv8"][2] >= 2 and split["conv8"][3] <= 148
+    assert split["ff2_8"][2] >= 2
+    assert split["qkv64"][2] == 1 and split["down8"][2] == 1   # full launches and stride-2 convs stay un-split
