@@ -183,6 +183,55 @@ def main():
     out["sched/shifted_betas"] = b_ref.numpy()
     print(f"shifted betas: reference vs oracle max abs {err:.2e}")
 
+    ref_sched.ShiftSNRScheduler.from_scheduler(_Sched(base), shift_mode="default", shift_scale=6.0, scheduler_class=_Cls)
+    out["sched/shifted_betas_default"] = captured["betas"].numpy()
+    t_all = torch.arange(base.shape[0])
+    snr_ref = ref_sched.compute_snr(t_all, _Sched(base))
+    assert (snr_ref - noise_schedule.snr_from_betas(base)).abs().max().item() <= 1e-6 * snr_ref.abs().max().item()
+    out["sched/snr"] = snr_ref.numpy()
+    rt = ref_sched.SNR_to_betas(snr_ref)
+    assert (torch.as_tensor(rt) - base).abs().max().item() < 1e-6  # SNR_to_betas inverts compute_snr
+    out["sched/betas_roundtrip"] = torch.as_tensor(rt).numpy()
+
+    # ---- 4. camera encoder, piece by piece --------------------------------------------------------------
+    with torch.no_grad():
+        rel_ref = rc.compute_relative_transform(src, tgt)
+        rel_orc = enc.relative_transform(src, tgt)
+    for key, b in zip(("R", "T"), rel_orc):  # camera_encoder.py:107-120 returns {"R": ..., "T": ...}
+        assert (rel_ref[key] - b).abs().max().item() < 1e-6, f"relative transform {key} differs"
+        out[f"camera/relative_{key}"] = rel_ref[key].numpy()
+    gx = torch.Generator().manual_seed(21)
+    for mod_name, ch in dims.items():
+        xm = torch.randn(src.shape[0], ch, 3, 4, generator=gx) * 1.7 - 0.2
+        with torch.no_grad():
+            a = rc.apply_modulation(xm, mod_name, e_ref)
+            b = enc.film(xm, mod_name, e_orc)
+        assert (a - b).abs().max().item() < 1e-5, f"FiLM at {mod_name} differs"
+        out[f"camera/film_all/{mod_name}"] = a.numpy()
+
+    # ---- 5. the look-at matrices the benchmark's synthetic cameras use (src/utils.py:51-85) --------------
+    import src.utils as ref_utils  # noqa: E402
+    import math
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import camera_matrix  # noqa: E402
+
+    ring = []
+    for V_ in (4, 8):
+        for i in range(V_):
+            az, el, r = math.radians(360.0 * i / V_), math.radians(20.0), 1.8
+            pos = [r * math.cos(el) * math.sin(az), r * math.sin(el), r * math.cos(el) * math.cos(az)]
+            m_ref = ref_utils.create_camera_matrix(pos, [0.0, 0.0, 0.0])
+            assert (m_ref - camera_matrix(360.0 * i / V_)).abs().max().item() < 1e-6
+            ring.append(m_ref.numpy())
+    out["utils/camera_ring"] = np.stack(ring)
+    print("camera pieces, FiLM at every modulator, look-at ring, SNR round trip: pinned")
+
+    old_path = os.path.join(GOLDEN, "reference_adapter.npz")
+    if os.path.exists(old_path):  # regenerating must not move any vector that is already committed
+        prev = np.load(old_path)
+        for k in prev.files:
+            assert k in out and np.array_equal(prev[k], out[k]), f"golden vector {k} changed"
     np.savez_compressed(os.path.join(GOLDEN, "reference_adapter.npz"), **out)
     print("wrote", os.path.join(GOLDEN, "reference_adapter.npz"),
           os.path.getsize(os.path.join(GOLDEN, "reference_adapter.npz")), "bytes")

@@ -130,3 +130,21 @@ def test_gemm_plan_pair_and_splitk_flags():
     assert split["conv8"][1] == 1 and split["conv8"][2] >= 2 and split["conv8"][3] <= 148
     assert split["ff2_8"][2] >= 2
     assert split["qkv64"][2] == 1 and split["down8"][2] == 1   # full launches and stride-2 convs stay un-split
+
+
+def test_product_scheduler_reproduces_reference_goldens():
+    """The product's own host-side scheduler math (mvd_b200/scheduler.py) against the vectors of the live reference
+    (src/training/scheduler.py; generated by oracle/gen_golden.py), not only against the oracle."""
+    import os
+
+    from mvd_b200 import scheduler as ps
+
+    golden = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_adapter.npz"))
+    base = mvd_b200.DDPMScheduler()
+    snr = ps.compute_snr(torch.arange(1000), base)
+    assert np.abs(snr.numpy() - golden["sched/snr"]).max() <= 1e-6 * float(golden["sched/snr"].max())
+    assert np.abs(ps.SNR_to_betas(snr).numpy() - golden["sched/betas_roundtrip"]).max() < 1e-6
+    for mode, key in (("interpolated", "sched/shifted_betas"), ("default", "sched/shifted_betas_default")):
+        s = mvd_b200.ShiftSNRScheduler.from_scheduler(mvd_b200.DDPMScheduler(), shift_mode=mode, shift_scale=6.0,
+                                                      scheduler_class=mvd_b200.DDPMScheduler)
+        assert np.abs(s.betas.numpy() - golden[key]).max() < 1e-7, mode

@@ -127,3 +127,42 @@ def test_oracle_tiny_unet_runs_and_names_match_reference_walk():
     keys = m.state_dict().keys()
     assert "base_unet.down_blocks.0.attentions.0.transformer_blocks.0.attn1.processor.to_out_ref.0.bias" in keys
     assert "image_encoder.unet.conv_in.weight" in keys and "camera_encoder.modulators.output.3.bias" in keys
+
+
+def test_oracle_camera_pieces_reproduce_reference():
+    """Relative pose (camera_encoder.py:107-120) and the FiLM of EVERY modulator (camera_encoder.py:198-255), on the
+    vectors the live reference produced (oracle/gen_golden.py section 4)."""
+    from oracle.gen_golden import build_camera_case
+
+    enc, src, tgt, proj, _, dims = build_camera_case()
+    with torch.no_grad():
+        r, t = enc.relative_transform(src, tgt)
+        e = enc.encode_cameras(src, tgt, proj)
+    assert np.abs(r.numpy() - GOLDEN["camera/relative_R"]).max() < 1e-6
+    assert np.abs(t.numpy() - GOLDEN["camera/relative_T"]).max() < 1e-6
+    gx = torch.Generator().manual_seed(21)
+    for name, ch in dims.items():
+        x = torch.randn(src.shape[0], ch, 3, 4, generator=gx) * 1.7 - 0.2
+        with torch.no_grad():
+            y = enc.film(x, name, e)
+        assert np.abs(y.numpy() - GOLDEN[f"camera/film_all/{name}"]).max() < 1e-5, name
+        assert (y - x).abs().max() > 1e-2
+
+
+def test_synthetic_camera_ring_is_the_references_look_at():
+    """tests/helpers.camera_matrix (the benchmark's synthetic cameras) == src/utils.py:51-85 create_camera_matrix."""
+    from helpers import camera_matrix
+
+    ring = [camera_matrix(360.0 * i / v) for v in (4, 8) for i in range(v)]
+    assert np.abs(torch.stack(ring).numpy() - GOLDEN["utils/camera_ring"]).max() < 1e-6
+
+
+def test_oracle_snr_and_default_shift_reproduce_reference():
+    from oracle import noise_schedule as ns
+
+    base = ns.sd21_betas()
+    snr = ns.snr_from_betas(base)
+    assert np.abs(snr.numpy() - GOLDEN["sched/snr"]).max() <= 1e-6 * float(GOLDEN["sched/snr"].max())
+    assert np.abs(ns.betas_from_snr(snr).numpy() - GOLDEN["sched/betas_roundtrip"]).max() < 1e-6
+    b = ns.shifted_betas(base, 6.0, "default")
+    assert np.abs(b.numpy() - GOLDEN["sched/shifted_betas_default"]).max() < 1e-7
