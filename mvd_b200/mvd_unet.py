@@ -46,8 +46,13 @@ class MultiViewUNet(nn.Module):
                  use_memory_efficient_attention: bool = True, enable_gradient_checkpointing: bool = True,
                  img_ref_scale: float = 0.3, cam_modulation_strength: float = 0.2, cam_output_dim: int = 1024,
                  cam_hidden_dim: int = 512, use_camera_conditioning: bool = True, use_image_conditioning: bool = True,
-                 simple_cam_encoder: bool = False, matched_batch_cfg: bool = False):
+                 simple_cam_encoder: bool = False, matched_batch_cfg: bool = False,
+                 cross_view_reference: bool = False):
         super().__init__()
+        # cross-view mode (north star / BASELINE configs[3]): every sample attends over the reference tokens of ALL
+        # views, passed to the processors as the 3-D reference [B, V*HW, C] of attention.py:95-132. Extension of the
+        # reference's constructor; off by default.
+        self.cross_view_reference = cross_view_reference
         self.use_camera_conditioning = use_camera_conditioning
         self.use_image_conditioning = use_image_conditioning
         self.cam_output_dim, self.cam_hidden_dim, self.simple_cam_encoder = cam_output_dim, cam_hidden_dim, simple_cam_encoder
@@ -162,7 +167,9 @@ class MultiViewUNet(nn.Module):
                 ref_batch_index = self._shard_index(shard, sample.shape[0], dev)
             else:
                 ref_batch_index = None
-                if self.matched_batch_cfg and sample.shape[0] > batch_size:
+                if self.cross_view_reference:
+                    features = self._cross_view_features(features, sample.shape[0])
+                elif self.matched_batch_cfg and sample.shape[0] > batch_size:
                     features = self._repeat_features(features, sample.shape[0] // batch_size)
             ref_hidden_states = self._map_image_features_to_attention_layers(features)
 
@@ -223,6 +230,23 @@ class MultiViewUNet(nn.Module):
             rep[name] = nchw_shape(v.repeat(times, 1, 1, 1))
         self.__dict__["_rep_cache"] = (key, rep, features)
         return rep
+
+    def _cross_view_features(self, features, batch: int):
+        """[V, C, H, W] per site -> the 3-D reference [batch, V*HW, C]: all views' tokens, the same for every sample.
+        (The reference-literal tensor: one copy per sample, so that the normalisation statistics of
+        attention.py:95-103 count exactly what they would count there.) Cached with the features."""
+        key = (id(features), batch)
+        cached = self.__dict__.get("_xview_cache")
+        if cached is not None and cached[0] == key and cached[2] is features:
+            return cached[1]
+        out = {}
+        for name, f in features.items():
+            if isinstance(f, tuple):
+                f = f[0]
+            v = nhwc_view(f)  # [V, H, W, C], dense
+            out[name] = v.reshape(1, -1, v.shape[-1]).repeat(batch, 1, 1)
+        self.__dict__["_xview_cache"] = (key, out, features)
+        return out
 
     def _map_image_features_to_attention_layers(self, image_features):
         ref_hidden_states = {}

@@ -206,13 +206,16 @@ class MultiViewUNetOracle(nn.Module):
 
     def __init__(self, unet_config: Optional[dict] = None, img_ref_scale=0.3, cam_modulation_strength=0.2,
                  cam_output_dim=1024, cam_hidden_dim=512, use_camera_conditioning=True, use_image_conditioning=True,
-                 matched_batch_cfg: bool = False):
+                 matched_batch_cfg: bool = False, cross_view_reference: bool = False):
         super().__init__()
         cfg = unet_config or {}
         self.base_unet = UNet2DConditionModel(**cfg)
         self.config = self.base_unet.config
         self.use_camera_conditioning, self.use_image_conditioning = use_camera_conditioning, use_image_conditioning
         self.matched_batch_cfg = matched_batch_cfg  # repeat per-view conditioning over CFG halves
+        # north-star / configs[3] mode: every sample attends over the reference tokens of ALL views, handed to the
+        # processors as the 3-D reference [B, V*HW, C] that attention.py:95-132 accepts
+        self.cross_view_reference = cross_view_reference
         ch = list(self.config.block_out_channels)
         dims = {f"down_{i}": ch[min(i, len(ch) - 1)] for i in range(len(self.base_unet.down_blocks))}
         dims.update({f"up_{i}": list(reversed(ch))[i] for i in range(len(self.base_unet.up_blocks))})
@@ -271,7 +274,10 @@ class MultiViewUNetOracle(nn.Module):
             elif text.shape[0] > nb:
                 ie_text = text[:nb]
             feats = self.image_features(source_image_latents, ie_text)
-            if self.matched_batch_cfg and sample.shape[0] > nb:
+            if self.cross_view_reference:
+                feats = {k: v.flatten(2).transpose(1, 2).reshape(1, -1, v.shape[1]).repeat(sample.shape[0], 1, 1)
+                         for k, v in feats.items()}
+            elif self.matched_batch_cfg and sample.shape[0] > nb:
                 feats = {k: v.repeat(sample.shape[0] // nb, 1, 1, 1) for k, v in feats.items()}
             ref = {a: f for n, f in feats.items() for a in self.feature_to_attention_map.get(n, [])}
         kw = dict(cross_attention_kwargs or {})

@@ -11,3 +11,5 @@ for flag in MVD_GEMM_2CTA MVD_GEMM_SPLITK; do
   env $flag=1 timeout 200 python profiles/gemm_bn_sweep.py 2>&1 | awk '{print $1,$2,$3,$4,$5,$6,$7,$8}' | tail -40
   env $flag=1 timeout 200 python bench.py 2>/dev/null | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('bench', d['value'], d['ms_per_step'])"
 done
+echo "=== cross-view model mode"
+MVD_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_model_gpu.py -x -q -k cross_view_reference_mode 2>&1 | tail -3
