@@ -7,6 +7,7 @@
 //           warps per CTA, up to 4 bulk groups in flight per warp, into a matrix with a 2560-byte row pitch
 //
 // Each is run with 1, 37, 74 and 148 CTAs (one per SM). Output: GB/s, bytes/clk/SM at the measured SM clock.
+// --mix: loads and stores together; --depth: load ring depth (4/8/12 boxes in flight) x private/shared source windows.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -I../../mvd_b200/csrc tma_bw.cu \
 //             ../../mvd_b200/csrc/host_common.cu -o tma_bw -lcuda
 #include <cstdio>
@@ -139,6 +140,37 @@ mix_kernel(const __grid_constant__ CUtensorMap map_ld, const __grid_constant__ C
   }
 }
 
+
+// Load throughput vs ring depth and sharing: DEPTH boxes of 16 KB in flight per CTA; `shared_rows` > 0 makes every
+// CTA walk the same `shared_rows`-row window (weight-like: the same lines are wanted by all SMs at about the same
+// time), 0 gives every CTA its own boxes (activation-like). Separates a per-SM ingest limit from an L2-side one.
+template <int DEPTH>
+__global__ void __launch_bounds__(128, 1)
+load_depth_kernel(const __grid_constant__ CUtensorMap map, int iters, int shared_rows, long long* cycles) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[DEPTH];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < DEPTH; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    for (int i = 0; i < iters + DEPTH; ++i) {
+      const int s = i % DEPTH;
+      if (i >= DEPTH) mbar_wait(&full[s], ((i - DEPTH) / DEPTH) & 1);
+      if (i < iters) {
+        mbar_arrive_expect_tx(&full[s], 128 * 128);
+        const int box = shared_rows > 0 ? i : blockIdx.x * iters + i;
+        const int row_tiles = shared_rows > 0 ? shared_rows / 128 : ROWS / 128;
+        tma_load_2d(smem + s * 16384, &map, &full[s], (box % (COLS / 64)) * 64, ((box / (COLS / 64)) % row_tiles) * 128);
+      }
+    }
+    cycles[blockIdx.x] = clock64() - t0;
+  }
+}
+
 static float time_ms(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, a, b);
@@ -146,7 +178,6 @@ static float time_ms(cudaEvent_t a, cudaEvent_t b) {
 }
 
 int main(int argc, char** argv) {
-  (void)argv;
   cudaDeviceProp prop;
   cudaGetDeviceProperties(&prop, 0);
   int clk_khz = 0;
@@ -175,6 +206,31 @@ int main(int argc, char** argv) {
   cudaEventCreate(&e1);
   const int iters = 2000;
 
+
+  if (argc > 1 && argv[1][0] == '-' && argv[1][1] == '-' && argv[1][2] == 'd') {  // --depth: ring depth x sharing
+    cudaFuncSetAttribute(load_depth_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384 + 2048);
+    cudaFuncSetAttribute(load_depth_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 16384 + 2048);
+    cudaFuncSetAttribute(load_depth_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 12 * 16384 + 2048);
+    std::vector<long long> hh(256);
+    for (int shared_rows : {0, 4096, 256}) {  // private boxes / a 10 MB window / a 0.6 MB window shared by all CTAs
+      for (int depth : {4, 8, 12}) {
+        for (int rep = 0; rep < 2; ++rep) {
+          if (depth == 4) load_depth_kernel<4><<<148, 128, 4 * 16384 + 2048>>>(map_ld, iters, shared_rows, cyc);
+          if (depth == 8) load_depth_kernel<8><<<148, 128, 8 * 16384 + 2048>>>(map_ld, iters, shared_rows, cyc);
+          if (depth == 12) load_depth_kernel<12><<<148, 128, 12 * 16384 + 2048>>>(map_ld, iters, shared_rows, cyc);
+          cudaDeviceSynchronize();
+        }
+        cudaMemcpy(hh.data(), cyc, 148 * sizeof(long long), cudaMemcpyDeviceToHost);
+        long long mx = 0;
+        for (int i = 0; i < 148; ++i) mx = hh[i] > mx ? hh[i] : mx;
+        printf("loads, 148 CTAs, %2d x 16 KB in flight, %-22s: %6.2f B/clk/SM\n", depth,
+               shared_rows == 0 ? "private boxes" : (shared_rows == 4096 ? "shared 10 MB window" : "shared 0.6 MB window"),
+               double(iters) * 16384 / double(mx));
+      }
+    }
+    printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+    return 0;
+  }
   if (argc > 1) {  // --mix: loads and stores together at 148 CTAs
     cudaFuncSetAttribute(mix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     long long* cyc2 = nullptr;
