@@ -5,6 +5,8 @@
 # Run under gpurun with a timeout; each variant is independent.
 set -u
 cd "$(dirname "$0")/.."
+echo "=== TMA load throughput vs ring depth / sharing"
+timeout 60 ./profiles/micro/tma_bw --depth 2>&1 | tail -12
 for flag in MVD_GEMM_2CTA MVD_GEMM_SPLITK; do
   echo "=== $flag=1"
   env $flag=1 timeout 300 python -m pytest tests/test_tc_kernels_gpu.py -x -q -k "linear or conv" 2>&1 | tail -3
