@@ -56,17 +56,23 @@ struct GemmArgs {
   unsigned int* ws_tickets;   // [tiles][4] arrival counters, one per 32-row warp slab; zero between launches
 };
 
-template <int BN, int CTAS = 1>
+constexpr int WS_MAX_KBLOCKS = 5;  // weight-stationary tiles: K <= 320
+
+// WS (weight-stationary, K <= 320): the CTA's weight tile [BN x K] stays in shared memory for the whole launch (every
+// CTA keeps ONE column tile: the grid is a multiple of the column-tile count) and only A streams through the ring.
+template <int BN, int CTAS = 1, bool WS = false>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = (BN / CTAS) * BK * 2;  // a CTA of a pair stages its half of the weight tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int B_RES_BYTES = WS ? WS_MAX_KBLOCKS * B_BYTES : 0;
+  static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;  // 64 KB
-  static constexpr int STAGES = CTAS == 2 ? ((BN <= 160) ? 6 : 5)
-                                          : (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
+  static constexpr int STAGES = WS ? 5
+                                : CTAS == 2 ? ((BN <= 160) ? 6 : 5)
+                                            : (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
   static_assert(STAGE_BYTES % 1024 == 0, "128B-swizzled tiles must stay 1024-byte aligned");
   static constexpr int BAR_BYTES = 1024;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + B_RES_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
   static constexpr int ACC_STRIDE = (BN <= 64) ? 64 : (BN <= 128) ? 128 : 256;
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
   static_assert(TOTAL <= 227 * 1024, "shared memory budget of one CTA");
@@ -93,12 +99,13 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // item is a (tile, k-slice); every CTA writes its fp32 partial rows to a workspace, and per 32-row slab the LAST
 // arriving warp (ticket counter, re-armed for the next launch) adds the slices in slice order — deterministic —
 // and runs the normal epilogue on the sum.
-template <int BN, bool S2, int CTAS, bool SPLIT = false>
+template <int BN, bool S2, int CTAS, bool SPLIT = false, bool WS = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                  const __grid_constant__ CUtensorMap mapRes, const GemmArgs p) {
-  using L = SmemLayout<BN, CTAS>;
+  using L = SmemLayout<BN, CTAS, WS>;
+  static_assert(!WS || (CTAS == 1 && !SPLIT && !S2), "weight-stationary tiles: single CTA, un-split, 1-tap only");
   // CTAS == 2: the grid is made of 2-CTA clusters; a pair computes a 256 x BN tile with cta_group::2 MMAs issued by
   // its even-ranked (leader) CTA. Every CTA loads its own 128 rows of A and its half of the weight tile, drains its
   // own 128 accumulator lanes and stores its own rows; only the barriers the MMA waits on live in the leader.
@@ -109,14 +116,16 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
   const int n_units = gridDim.x / CTAS;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* epi_smem = smem + L::STAGES * L::STAGE_BYTES;
+  [[maybe_unused]] uint8_t* b_res = smem + L::STAGES * L::STAGE_BYTES;  // WS: resident weight tile, k-block major
+  uint8_t* epi_smem = smem + L::STAGES * L::STAGE_BYTES + L::B_RES_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + L::EPI_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + L::STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * L::STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint64_t* res_bar = tmem_empty + 2;          // [EPI_WARPS][EPI_BUFS]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS * EPI_BUFS);
+  uint64_t* b_full = res_bar + EPI_WARPS * EPI_BUFS;  // WS: the resident weight tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);  // provably warp-uniform role index
   const int lane = threadIdx.x & 31;
@@ -135,6 +144,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_init(&tmem_empty[a], 4 * CTAS);  // the epilogue warps of every CTA of the pair
     }
     for (int i = 0; i < EPI_WARPS * EPI_BUFS; ++i) mbar_init(&res_bar[i], 1);
+    if constexpr (WS) mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -164,6 +174,13 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t lead_full = PAIR ? mapa_shared(smem_u32(&full[0]), 0) : 0u;  // leader's full[] barriers
+      if constexpr (WS) {
+        // gridDim.x is a multiple of tiles_n, so t % tiles_n is the same for every tile of this CTA
+        const int n_tile_fixed = static_cast<int>(blockIdx.x) % p.tiles_n;
+        mbar_arrive_expect_tx(b_full, static_cast<uint32_t>(k_blocks) * L::B_BYTES);
+        for (int kb = 0; kb < k_blocks; ++kb)
+          tma_load_2d(b_res + kb * L::B_BYTES, &mapB, b_full, kb * BK, n_tile_fixed * BN);
+      }
       for (int t = unit; t < p.tiles_total; t += n_units) {
         const int tile = SPLIT ? t / p.splits : t;
         const int ks = SPLIT ? t - tile * p.splits : 0;
@@ -203,6 +220,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                   tma_load_4d_pair(sa, &mapA2, fb, (kc - p.kc_a1) * BK, x0 + kx - 1, y0 + ky - 1, n0);
               }
               tma_load_2d_pair(sb, &mapB, fb, tap * p.cin + kc * BK, n_tile * BN + static_cast<int>(rank) * (BN / 2));
+            } else if constexpr (WS) {
+              mbar_arrive_expect_tx(&full[stage], L::A_BYTES);
+              tma_load_4d(sa, &mapA, &full[stage], kc * BK, x0 + kx - 1, y0 + ky - 1, n0);
             } else {
               mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
               if constexpr (S2) {
@@ -236,6 +256,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
+    if constexpr (WS) {
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+    }
     for (int t = unit; t < p.tiles_total; t += n_units, ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
@@ -250,7 +274,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
         const uint64_t adesc = umma_desc_sw128(sa);
-        const uint64_t bdesc = umma_desc_sw128(sa + L::A_BYTES);
+        const uint64_t bdesc = WS ? umma_desc_sw128(smem_base + L::STAGES * L::STAGE_BYTES + kb * L::B_BYTES)
+                                  : umma_desc_sw128(sa + L::A_BYTES);
         if (elect_one()) {
           // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
           if constexpr (PAIR) {
@@ -567,6 +592,15 @@ static bool pair_enabled() {
   return on;
 }
 
+// Weight-stationary tiles for K <= 320 linears: EXPERIMENTAL, off unless MVD_GEMM_WS=1 — not yet run on hardware.
+static bool ws_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MVD_GEMM_WS");
+    return e != nullptr && e[0] == '1';
+  }();
+  return on;
+}
+
 // Split-K: EXPERIMENTAL, off unless MVD_GEMM_SPLITK=1 and the caller registered a workspace
 // (mvd_gemm_set_workspace) — not yet run on hardware.
 static bool splitk_enabled() {
@@ -655,6 +689,26 @@ static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUten
   return MVD_OK;
 }
 
+static int launch_ws(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
+                     const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
+  using L = SmemLayout<128, 1, true>;
+  static bool configured = false;
+  if (!configured) {
+    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<128, false, 1, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  // every CTA keeps one column tile: grid = tiles_n * (row groups that fit on the machine)
+  const int tiles_m = args.tiles_total / args.tiles_n;
+  int groups = sm_count() / args.tiles_n;
+  if (groups > tiles_m) groups = tiles_m;
+  MVD_CUDA(launch_pdl(gemm_conv_kernel<128, false, 1, false, true>, dim3(groups * args.tiles_n), dim3(GEMM_THREADS),
+                      L::TOTAL, stream, mA, mA2, mB, mO, mR, args));
+  MVD_CUDA(cudaGetLastError());
+  count_launches(1);
+  return MVD_OK;
+}
+
 template <int BN>
 static int launch_split(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
                         const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
@@ -716,8 +770,10 @@ static int pick_bn_pair(int N, int M_tiles, int force_bn, int single_bn) {
 struct GemmPlan {
   int TW, TH, TN, tiles_m;
   int bn, ctas, splits;
+  bool ws;  // weight-stationary 128-wide tiles (grid must then be a multiple of the column-tile count)
 };
-static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, int stride, int geglu, int force_bn) {
+static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, int stride, int geglu, int force_bn,
+                          bool two_source) {
   GemmPlan pl;
   pick_tile(Nimg, H, W, &pl.TW, &pl.TH, &pl.TN);
   pl.tiles_m = ((W + pl.TW - 1) / pl.TW) * ((H + pl.TH - 1) / pl.TH) * ((Nimg + pl.TN - 1) / pl.TN);
@@ -726,7 +782,13 @@ static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, 
   pl.ctas = pair_bn > 0 ? 2 : 1;
   if (pair_bn > 0) pl.bn = pair_bn;
   pl.splits = 1;
-  if (pl.ctas == 1 && force_bn == 0 && !geglu && stride == 1) {
+  // weight-stationary: 1-tap, K <= 320, N a multiple of 128 (GEGLU: only with the 128-wide interleave), enough row
+  // tiles that every CTA amortises its resident weight tile over several of them
+  pl.ws = ws_enabled() && pl.ctas == 1 && ntaps == 1 && stride == 1 && Cin <= WS_MAX_KBLOCKS * BK &&
+          Cout % 128 == 0 && (force_bn == 0 || force_bn == 128) && (!geglu || force_bn == 128) &&
+          !two_source && Cout / 128 <= sm_count() && pl.tiles_m * (Cout / 128) >= 4 * sm_count();
+  if (pl.ws) pl.bn = 128;
+  if (!pl.ws && pl.ctas == 1 && force_bn == 0 && !geglu && stride == 1) {
     int bn_split = pl.bn;
     pick_splitk(Cout, pl.tiles_m, ntaps * (Cin / 64), pl.bn, &bn_split, &pl.splits);
     if (pl.splits > 1) pl.bn = bn_split;
@@ -763,7 +825,7 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  const GemmPlan pl = plan_gemm(Nimg, H, W, Cin, Cout, ntaps, stride, geglu, force_bn);
+  const GemmPlan pl = plan_gemm(Nimg, H, W, Cin, Cout, ntaps, stride, geglu, force_bn, a2 != nullptr);
   const int TW = pl.TW, TH = pl.TH, TN = pl.TN;
   g.TW = TW; g.TH = TH; g.TN = TN;
   g.tiles_x = (W + TW - 1) / TW;
@@ -858,6 +920,7 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
     }
   }
 
+  if (pl.ws) return launch_ws(mA, mA2, mB, mO, mR, g, stream);
   if (splits > 1) {
     switch (BN) {
       case 64: return launch_split<64>(mA, mA2, mB, mO, mR, g, stream);
@@ -898,13 +961,20 @@ int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntap
   MVD_CHECK(n_img > 0 && h_out > 0 && w_out > 0 && c_in > 0 && c_in % 64 == 0 && c_out > 0 && c_out % 32 == 0 &&
                 (ntaps == 1 || ntaps == 9) && (stride == 1 || stride == 2),
             "gemm_plan: unsupported problem");
-  const GemmPlan pl = plan_gemm(n_img, h_out, w_out, c_in, c_out, ntaps, stride, geglu, tile_n);
+  const GemmPlan pl = plan_gemm(n_img, h_out, w_out, c_in, c_out, ntaps, stride, geglu, tile_n, false);
   const int units = ((c_out + pl.bn - 1) / pl.bn) * ((pl.tiles_m + pl.ctas - 1) / pl.ctas) * pl.splits;
   const int cap = sm_count() / pl.ctas;
   if (bn) *bn = pl.bn;
   if (ctas) *ctas = pl.ctas;
   if (splits) *splits = pl.splits;
-  if (grid) *grid = (units < cap ? units : cap) * pl.ctas;
+  if (grid) {
+    *grid = (units < cap ? units : cap) * pl.ctas;
+    if (pl.ws) {
+      const int tn = c_out / 128;
+      const int groups = sm_count() / tn < pl.tiles_m ? sm_count() / tn : pl.tiles_m;
+      *grid = groups * tn;
+    }
+  }
   return MVD_OK;
 }
 

@@ -20,6 +20,7 @@ There is no PyTorch compute fallback: CPU tensors or a missing shared library ra
 from __future__ import annotations
 
 import inspect
+import os
 from typing import Any, Dict, Optional, Tuple
 
 import torch
@@ -43,7 +44,9 @@ SD21_CONFIG = dict(
     up_has_attn=(False, True, True, True),
 )
 
-GEGLU_TILE = 256  # tile width the GEGLU weight interleave is built for (ops.linear(..., geglu=True, tile_n=...))
+# tile width the GEGLU weight interleave is built for (ops.linear(..., geglu=True, tile_n=...)); 128 only for the
+# experimental weight-stationary GEMM tiles (MVD_GEMM_WS=1), which are 128 wide
+GEGLU_TILE = 128 if os.environ.get("MVD_GEGLU_TILE", "256") == "128" else 256
 
 
 class _Config(dict):

@@ -130,6 +130,10 @@ def test_gemm_plan_pair_and_splitk_flags():
     assert split["conv8"][1] == 1 and split["conv8"][2] >= 2 and split["conv8"][3] <= 148
     assert split["ff2_8"][2] >= 2
     assert split["qkv64"][2] == 1 and split["down8"][2] == 1   # full launches and stride-2 convs stay un-split
+    ws = _plans({"MVD_GEMM_WS": "1"})
+    assert ws["qkv64"] == [128, 1, 1, 140]            # 10 column tiles x 14 row groups: every CTA keeps one weight tile
+    assert ws["proj64"][0] == 160 and ws["geglu64"][0] == 256   # N = 320 and the 256-wide GEGLU interleave stay as they are
+    assert ws["conv64"][0] == 160 and ws["ff2_8"] == [64, 1, 1, 80]
 
 
 def test_product_scheduler_reproduces_reference_goldens():
