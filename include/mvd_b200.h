@@ -59,18 +59,12 @@ int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const vo
                      const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
                      int w_out, int c_out, int stride, int tile_n, void* stream);
 
-/* Optional scratch for split-K GEMMs (problems with fewer output tiles than SMs, e.g. the 8x8-latent level of the
- * UNet). Registers, for the CALLING HOST THREAD, a device buffer that subsequent mvd_linear_bf16 / mvd_conv3x3_bf16
- * calls may use while they run; it must be zero-filled once, stay valid until those kernels finish, and must not be
- * shared by launches that can run concurrently. NULL unregisters. Without a workspace (or without MVD_GEMM_SPLITK=1:
- * the split-K path is experimental) every GEMM runs un-split. No reference analogue (scheduling detail). */
-int mvd_gemm_set_workspace(void* workspace, int64_t bytes);
-
 /* The scheduling decision mvd_linear_bf16 (n_img = h_out = 1, w_out = M, ntaps = 1) / mvd_conv3x3_bf16 (ntaps = 9)
- * would take for a problem, without launching anything: tile width, CTAs per tile (2 = cta_group::2 pair), k-slices
- * and grid size. Any output pointer may be NULL. For tests and tuning; no reference analogue. */
+ * would take for a problem, without launching anything: tile width, whether the weight tile stays resident in shared
+ * memory (weight-stationary tiles of the K <= 320 linears) and the grid size. Any output pointer may be NULL. For
+ * tests and tuning; no reference analogue. */
 int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntaps, int stride, int geglu, int tile_n,
-                  int* bn, int* ctas, int* splits, int* grid);
+                  int* bn, int* weight_stationary, int* grid);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Fused flash-attention forward, head_dim 64 (tcgen05 + TMEM + TMA), csrc/attn.cu

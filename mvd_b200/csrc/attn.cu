@@ -1240,6 +1240,391 @@ attn_fwd4_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   }
 }
 
+
+// ================================================================================================
+// Fifth generation (two tiles, two softmax warpgroups as attn_fwd3_kernel) built on what the round-2 traces showed
+// (profiles/r2_attn_variants*.txt): the kernel is bound by the SERIAL chain of one softmax warp per KV block
+// (S wait -> TMEM load -> row max -> exponentials -> P store; 2830 of a 2940-cycle period), in which the MUFU only
+// runs during the exponentials. Changes:
+//  * look-ahead row maximum: while a warp exponentiates block j it streams S(j+1) — already complete in TMEM —
+//    through a 32-register window and folds it into the maximum of the NEXT block. At the top of block j+1 the
+//    reference maximum is known before S is loaded, so the exponentials start as soon as the registers land; the
+//    row-max pass leaves the chain (exact: same maxima as before, S is simply read twice from TMEM).
+//  * P is published in two halves (p_half[t][0/1]); the PV MMA is issued as two groups of 4 k-steps, so PV(j) has
+//    finished ~1/2 block earlier and the wait for PV(j-1) before the first P store of block j never stalls.
+//  * MMA issue order follows the half-period phase shift of the two warpgroups and doubles as the restoring force
+//    towards it:  PV_B(j-1).h0  QK_A(j+1)  PV_A(j).h0  PV_B(j-1).h1  QK_B(j+1)  PV_A(j).h1
+// ================================================================================================
+template <int POLY8, bool TRACE>
+__global__ void __launch_bounds__(384, 1)
+attn_fwd5_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                 const __grid_constant__ CUtensorMap mapV, const AttnArgs p, long long* trace) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;  // two tiles
+  uint8_t* sK = smem + 2 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT2_KS * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT2_KS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                   // [1]
+  uint64_t* k_full = bars + 1;               // [KS]
+  uint64_t* k_empty = k_full + ATT2_KS;      // [KS]
+  uint64_t* v_full = k_empty + ATT2_KS;      // [KS]
+  uint64_t* v_empty = v_full + ATT2_KS;      // [KS]
+  uint64_t* s_full = v_empty + ATT2_KS;      // [2] per tile
+  uint64_t* p_half = s_full + 2;             // [2][2] per tile, per half of the KV block
+  uint64_t* o_final = p_half + 4;            // [1]
+  uint64_t* s_free = o_final + 1;            // [2] per tile: S_t has been read into registers
+  uint64_t* pv_done = s_free + 2;            // [2] per tile: PV_t(j) (both halves) complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pv_done + 2);
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int q_pair = blockIdx.x;
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int n_blocks = (p.Skv + ATT_BN - 1) / ATT_BN;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < ATT2_KS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_half[t * 2], 4);
+      mbar_init(&p_half[t * 2 + 1], 4);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&pv_done[t], 1);
+    }
+    mbar_init(o_final, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+        tma_load_3d(sQ, &mapQ, q_full, head * ATT_D, q_pair * 256, batch);
+        tma_load_3d(sQ + ATT_TILE_BYTES, &mapQ, q_full, head * ATT_D, q_pair * 256 + 128, batch);
+        for (int j = 0; j < n_blocks; ++j) {
+          const int s = j % ATT2_KS;
+          const uint32_t ph = (j / ATT2_KS) & 1;
+          mbar_wait(&k_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+          tma_load_3d(sK + s * ATT_TILE_BYTES, &mapK, &k_full[s], head * ATT_D, j * ATT_BN, batch);
+          mbar_wait(&v_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+          tma_load_3d(sV + s * ATT_TILE_BYTES, &mapV, &v_full[s], head * ATT_D, j * ATT_BN, batch);
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer (warp-uniform control flow, one elected lane issues) =====================
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, false, /*b_mn_major=*/true);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t q_addr = __shfl_sync(0xffffffffu, smem_u32(sQ), 0);
+      const uint32_t k_addr = __shfl_sync(0xffffffffu, smem_u32(sK), 0);
+      const uint32_t v_addr = __shfl_sync(0xffffffffu, smem_u32(sV), 0);
+      auto issue_qk = [&](int t, int j, bool release_k) {  // S_t = Q_t K_j^T
+        const uint64_t qdesc = umma_desc_sw128(q_addr + t * ATT_TILE_BYTES);
+        const uint64_t kdesc = umma_desc_sw128(k_addr + (j % ATT2_KS) * ATT_TILE_BYTES);
+        const uint32_t d = tb + tm2_s(t);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[t]);
+          if (release_k) umma_commit(&k_empty[j % ATT2_KS]);
+        }
+        __syncwarp();
+      };
+      // O_t += P_t[:, 64 h : 64 h + 64] V_j[64 h : 64 h + 64, :]   (4 k-steps of 16)
+      auto issue_pv = [&](int t, int j, int h, bool release_v) {
+        const uint64_t vdesc = umma_desc_sw128(v_addr + (j % ATT2_KS) * ATT_TILE_BYTES);
+        const uint32_t a_tmem = tb + tm2_p(t);
+        const uint32_t d = tb + tm2_o(t);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 4 * h; k < 4 * h + 4; ++k)
+            umma_ts(d, a_tmem + 8 * k, vdesc + 128 * k, idesc_pv, (j != 0 || k != 0) ? 1u : 0u);
+          if (h == 1) umma_commit(&pv_done[t]);
+          if (release_v) umma_commit(&v_empty[j % ATT2_KS]);
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_qk(0, 0, false);
+      issue_qk(1, 0, true);
+      for (int j = 0; j < n_blocks; ++j) {
+        const uint32_t par = j & 1;
+        const bool more = j + 1 < n_blocks;
+        if (j > 0) {
+          mbar_wait(&p_half[2], par ^ 1);
+          tc_fence_after();
+          issue_pv(1, j - 1, 0, false);
+        }
+        if (more) {
+          mbar_wait(&k_full[(j + 1) % ATT2_KS], ((j + 1) / ATT2_KS) & 1);
+          mbar_wait(&s_free[0], par);
+          tc_fence_after();
+          issue_qk(0, j + 1, false);
+        }
+        mbar_wait(&v_full[j % ATT2_KS], (j / ATT2_KS) & 1);
+        mbar_wait(&p_half[0], par);
+        tc_fence_after();
+        issue_pv(0, j, 0, false);
+        if (j > 0) {
+          mbar_wait(&p_half[3], par ^ 1);
+          tc_fence_after();
+          issue_pv(1, j - 1, 1, true);
+        }
+        if (more) {
+          mbar_wait(&s_free[1], par);
+          tc_fence_after();
+          issue_qk(1, j + 1, true);
+        }
+        mbar_wait(&p_half[1], par);
+        tc_fence_after();
+        issue_pv(0, j, 1, false);
+      }
+      mbar_wait(&p_half[2], (n_blocks - 1) & 1);
+      tc_fence_after();
+      issue_pv(1, n_blocks - 1, 0, false);
+      mbar_wait(&p_half[3], (n_blocks - 1) & 1);
+      tc_fence_after();
+      issue_pv(1, n_blocks - 1, 1, true);
+      if (elect_one()) umma_commit(o_final);
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax warpgroups (warps 4..7: tile A, 8..11: tile B) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t t_s = tmem_base + tm2_s(t) + lane_off;
+    const uint32_t t_p = tmem_base + tm2_p(t) + lane_off;
+    const uint32_t t_o = tmem_base + tm2_o(t) + lane_off;
+    const bool tracer = TRACE && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && q == 0 && lane == 0;
+    long long* tr = trace + t * 8 * 64;
+    float m_ref = -INFINITY;
+    float l = 0.f;
+    float mxn0 = -INFINITY, mxn1 = -INFINITY;  // running maximum of the NEXT block (raw scores)
+
+    // folds 32 raw score columns [c0, c0 + 32) of block jb, held in the window, into the look-ahead maximum
+    auto fold_window = [&](const uint32_t* win, int jb, int c0) {
+      const int valid = p.Skv - jb * ATT_BN - c0;  // columns >= valid are padding (last block only)
+      if (valid >= 32) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 4) {
+          mxn0 = max3f(mxn0, __uint_as_float(win[c]), __uint_as_float(win[c + 1]));
+          mxn1 = max3f(mxn1, __uint_as_float(win[c + 2]), __uint_as_float(win[c + 3]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          if (c < valid) mxn0 = fmaxf(mxn0, __uint_as_float(win[c]));
+      }
+    };
+
+    // prologue: maximum of block 0 (the only one that is not hidden behind exponentials)
+    mbar_wait(&s_full[t], 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < ATT_BN; c0 += 32) {
+      uint32_t win[32];
+      tmem_ld_32x32b_x32(t_s + c0, win);
+      tmem_ld_wait();
+      fold_window(win, 0, c0);
+    }
+
+    for (int j = 0; j < n_blocks; ++j) {
+      if (tracer && j < 64) tr[j * 8 + 0] = clock64();
+      // S_t(j) is complete: block 0 was waited for above, block j > 0 by the look-ahead of block j - 1
+      float x[ATT_BN];
+      {
+        uint32_t* xr = reinterpret_cast<uint32_t*>(x);
+        tmem_ld_32x32b_x32(t_s + 0, xr + 0);
+        tmem_ld_32x32b_x32(t_s + 32, xr + 32);
+        tmem_ld_32x32b_x32(t_s + 64, xr + 64);
+        tmem_ld_32x32b_x32(t_s + 96, xr + 96);
+      }
+      const float mx = fmaxf(mxn0, mxn1) * p.scale_log2;
+      mxn0 = -INFINITY;
+      mxn1 = -INFINITY;
+      const bool need = mx > m_ref + LAZY_RESCALE_THRESHOLD;
+      float alpha = 1.f;
+      if (need) {
+        alpha = ex2_approx(m_ref - mx);
+        m_ref = mx;
+      }
+      const bool any_need = __any_sync(0xffffffffu, need);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[t]);
+      if (tracer && j < 64) tr[j * 8 + 1] = clock64();
+      const int valid = p.Skv - j * ATT_BN;
+      if (valid < ATT_BN) {
+#pragma unroll
+        for (int c = 0; c < ATT_BN; ++c) x[c] = (c < valid) ? x[c] : -INFINITY;
+      }
+      const float2 neg_m2 = make_float2(-m_ref, -m_ref);
+      const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
+      float2* x2 = reinterpret_cast<float2*>(x);
+      float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+      const bool look = j + 1 < n_blocks;
+      uint32_t win[32];
+
+      // exponentials of 16 score columns [16 * sc, 16 * sc + 16) -> 8 packed registers pk[0..8)
+      auto exp16 = [&](int sc, uint32_t* pk) {
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+          const int i0 = sc * 8 + i;  // pair index 0..63
+          const float2 a0 = ffma2(x2[i0], scale2, neg_m2), a1 = ffma2(x2[i0 + 1], scale2, neg_m2);
+          float2 e0, e1;
+          if ((i0 & 7) < POLY8) e0 = ex2_poly2(a0);
+          else e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+          if (((i0 + 1) & 7) < POLY8) e1 = ex2_poly2(a1);
+          else e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+          acc0 = fadd2(acc0, e0);
+          acc1 = fadd2(acc1, e1);
+          pk[i] = pack_bf16x2(e0.x, e0.y);
+          pk[i + 1] = pack_bf16x2(e1.x, e1.y);
+        }
+      };
+
+      // ---- first half of the block: columns 0..63
+      {
+        uint32_t pk[16];
+        exp16(0, pk);
+        exp16(1, pk + 8);
+        // P_t and O_t may only be touched once PV_t(j-1) has completed (its second half was issued at the end of
+        // block j-1 and is 4 MMAs long)
+        if (j > 0) {
+          mbar_wait(&pv_done[t], (j - 1) & 1);
+          tc_fence_after();
+          if (any_need) {  // rare (lazy rescaling): 8 columns at a time, few registers
+#pragma unroll 1
+            for (int c0 = 0; c0 < ATT_D; c0 += 8) {
+              uint32_t o[8];
+              tmem_ld_32x32b_x8(t_o + c0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tmem_st_32x32b_x8(t_o + c0, o);
+            }
+          }
+        }
+        tmem_st_32x32b_x16(t_p + 0, pk);
+        exp16(2, pk);
+        exp16(3, pk + 8);
+        tmem_st_32x32b_x16(t_p + 16, pk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_half[t * 2]);
+      if (tracer && j < 64) tr[j * 8 + 2] = clock64();
+
+      // ---- second half: columns 64..127, interleaved with the look-ahead maximum of block j+1
+      if (look) {
+        mbar_wait(&s_full[t], (j + 1) & 1);
+        tc_fence_after();
+        tmem_ld_32x32b_x32(t_s + 0, win);
+      }
+      if (tracer && j < 64) tr[j * 8 + 3] = clock64();
+      {
+        uint32_t pk[16];
+        exp16(4, pk);
+        if (look) {
+          tmem_ld_wait();
+          fold_window(win, j + 1, 0);
+          tmem_ld_32x32b_x32(t_s + 32, win);
+        }
+        exp16(5, pk + 8);
+        tmem_st_32x32b_x16(t_p + 32, pk);
+        if (look) {
+          tmem_ld_wait();
+          fold_window(win, j + 1, 32);
+          tmem_ld_32x32b_x32(t_s + 64, win);
+        }
+        exp16(6, pk);
+        if (look) {
+          tmem_ld_wait();
+          fold_window(win, j + 1, 64);
+          tmem_ld_32x32b_x32(t_s + 96, win);
+        }
+        exp16(7, pk + 8);
+        tmem_st_32x32b_x16(t_p + 48, pk);
+      }
+      if (tracer && j < 64) tr[j * 8 + 4] = clock64();
+      l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_half[t * 2 + 1]);
+      if (look) {
+        tmem_ld_wait();
+        fold_window(win, j + 1, 96);
+      }
+      if (tracer && j < 64) tr[j * 8 + 5] = clock64();
+    }
+
+    mbar_wait(o_final, 0);
+    tc_fence_after();
+    {
+      uint32_t o[ATT_D];
+      tmem_ld_32x32b_x32(t_o, o);
+      tmem_ld_32x32b_x32(t_o + 32, o + 32);
+      tmem_ld_wait();
+      const float inv_l = 1.f / l;
+      const int row = q_pair * 256 + t * 128 + row_in_tile;
+      if (row < p.Sq) {
+        __nv_bfloat16* dst = p.out + static_cast<int64_t>(batch) * p.o_batch_stride +
+                             static_cast<int64_t>(row) * p.ldo + head * ATT_D;
+#pragma unroll
+        for (int c = 0; c < ATT_D; c += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(__uint_as_float(o[c + 0]) * inv_l, __uint_as_float(o[c + 1]) * inv_l);
+          v.y = pack_bf16x2(__uint_as_float(o[c + 2]) * inv_l, __uint_as_float(o[c + 3]) * inv_l);
+          v.z = pack_bf16x2(__uint_as_float(o[c + 4]) * inv_l, __uint_as_float(o[c + 5]) * inv_l);
+          v.w = pack_bf16x2(__uint_as_float(o[c + 6]) * inv_l, __uint_as_float(o[c + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(dst + c) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
 }  // namespace mvd
 
 extern "C" int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_stride, const void* k, int64_t ldk,
@@ -1288,7 +1673,24 @@ extern "C" int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_st
   const bool two_tiles = (s_q >= 512) && (static_cast<long>((s_q + 255) / 256) * heads * batch >= 2L * sm_count());
   const char* var_env = getenv("MVD_ATTN_VARIANT");
   const int variant = var_env ? atoi(var_env) : 0;
-  if (two_tiles && variant >= 4000) {
+  if (two_tiles && variant >= 5000) {
+    dim3 grid((s_q + 255) / 256, heads, batch);
+    long long* trace = reinterpret_cast<long long*>(getenv("MVD_ATTN_TRACE_PTR") ? strtoull(getenv("MVD_ATTN_TRACE_PTR"), nullptr, 0) : 0ull);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define MVD_A5(POLY, TR)                                                                                             \
+  do {                                                                                                               \
+    MVD_CUDA(cudaFuncSetAttribute(attn_fwd5_kernel<POLY, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM)); \
+    MVD_CUDA(launch_pdl(attn_fwd5_kernel<POLY, TR>, grid, dim3(384), ATT2_SMEM, st, mQ, mK, mV, a, trace));           \
+  } while (0)
+    const int poly = variant % 10;
+    const bool tr = (variant % 1000) >= 100 && trace != nullptr;
+    if (tr) { if (poly == 0) MVD_A5(0, true); else MVD_A5(1, true); }
+    else if (poly == 0) MVD_A5(0, false);
+    else if (poly == 1) MVD_A5(1, false);
+    else if (poly == 2) MVD_A5(2, false);
+    else MVD_A5(3, false);
+#undef MVD_A5
+  } else if (two_tiles && variant >= 4000) {
     dim3 grid((s_q + 255) / 256, heads, batch);
     long long* trace = reinterpret_cast<long long*>(getenv("MVD_ATTN_TRACE_PTR") ? strtoull(getenv("MVD_ATTN_TRACE_PTR"), nullptr, 0) : 0ull);
     cudaStream_t st = static_cast<cudaStream_t>(stream);

@@ -50,26 +50,20 @@ struct GemmArgs {
   int img_max;           // clamp for the img index (padded rows of the last tile)
   const __nv_bfloat16* bias;  // [N] (permuted like the weight rows when geglu)
   const float* img_bias;      // [imgs, img_bias_ld] fp32 (e.g. time-embedding projection)
-  // split-K (SPLIT kernels only): tiles_total counts (tile, k-slice) work items, slice fastest
-  int splits;                 // k-slices per output tile
-  float* ws_partial;          // [tiles][splits][128][BN] fp32 partial accumulators
-  unsigned int* ws_tickets;   // [tiles][4] arrival counters, one per 32-row warp slab; zero between launches
 };
 
 constexpr int WS_MAX_KBLOCKS = 5;  // weight-stationary tiles: K <= 320
 
 // WS (weight-stationary, K <= 320): the CTA's weight tile [BN x K] stays in shared memory for the whole launch (every
 // CTA keeps ONE column tile: the grid is a multiple of the column-tile count) and only A streams through the ring.
-template <int BN, int CTAS = 1, bool WS = false>
+template <int BN, bool WS = false>
 struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = (BN / CTAS) * BK * 2;  // a CTA of a pair stages its half of the weight tile
+  static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int B_RES_BYTES = WS ? WS_MAX_KBLOCKS * B_BYTES : 0;
   static constexpr int STAGE_BYTES = WS ? A_BYTES : A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = EPI_WARPS * EPI_BUFS * EPI_BUF_BYTES;  // 64 KB
-  static constexpr int STAGES = WS ? 5
-                                : CTAS == 2 ? ((BN <= 160) ? 6 : 5)
-                                            : (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
+  static constexpr int STAGES = WS ? 5 : (BN <= 64) ? 6 : (BN <= 128) ? 5 : (BN <= 160) ? 4 : 3;
   static_assert(STAGE_BYTES % 1024 == 0, "128B-swizzled tiles must stay 1024-byte aligned");
   static constexpr int BAR_BYTES = 1024;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + B_RES_BYTES + EPI_BYTES + BAR_BYTES + 1024 /*align slack*/;
@@ -95,25 +89,18 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 
-// SPLIT: split-K for problems with fewer output tiles than SMs (the 8x8-latent level: M = 512 rows). Each work
-// item is a (tile, k-slice); every CTA writes its fp32 partial rows to a workspace, and per 32-row slab the LAST
-// arriving warp (ticket counter, re-armed for the next launch) adds the slices in slice order — deterministic —
-// and runs the normal epilogue on the sum.
-template <int BN, bool S2, int CTAS, bool SPLIT = false, bool WS = false>
+// Round 2 measured and removed two variants of this kernel (profiles/r2_gemm_variants.txt): CTA-pair tiles
+// (cta_group::2, 256 x BN; 5-20 % slower at every M = 32768 linear, step 13.74 vs 13.26 ms) and split-K for the
+// under-filled 8x8 level (the fp32 fix-up traffic cost more than the idle SMs: 30.6 vs 13.8 us at N=1280, K=2560).
+template <int BN, bool S2, bool WS = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                  const __grid_constant__ CUtensorMap mapRes, const GemmArgs p) {
-  using L = SmemLayout<BN, CTAS, WS>;
-  static_assert(!WS || (CTAS == 1 && !SPLIT && !S2), "weight-stationary tiles: single CTA, un-split, 1-tap only");
-  // CTAS == 2: the grid is made of 2-CTA clusters; a pair computes a 256 x BN tile with cta_group::2 MMAs issued by
-  // its even-ranked (leader) CTA. Every CTA loads its own 128 rows of A and its half of the weight tile, drains its
-  // own 128 accumulator lanes and stores its own rows; only the barriers the MMA waits on live in the leader.
-  constexpr bool PAIR = CTAS == 2;
-  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-  const bool leader = rank == 0;
-  const int unit = blockIdx.x / CTAS;  // scheduling unit (CTA or CTA pair) and their number
-  const int n_units = gridDim.x / CTAS;
+  using L = SmemLayout<BN, WS>;
+  static_assert(!WS || !S2, "weight-stationary tiles: 1-tap only");
+  const int unit = blockIdx.x;
+  const int n_units = gridDim.x;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   [[maybe_unused]] uint8_t* b_res = smem + L::STAGES * L::STAGE_BYTES;  // WS: resident weight tile, k-block major
@@ -141,28 +128,18 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4 * CTAS);  // the epilogue warps of every CTA of the pair
+      mbar_init(&tmem_empty[a], 4);
     }
     for (int i = 0; i < EPI_WARPS * EPI_BUFS; ++i) mbar_init(&res_bar[i], 1);
     if constexpr (WS) mbar_init(b_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    if constexpr (PAIR) {
-      tmem_alloc_pair(tmem_slot, L::TMEM_COLS);
-      tmem_relinquish_pair();
-    } else {
-      tmem_alloc(tmem_slot, L::TMEM_COLS);
-      tmem_relinquish();
-    }
+    tmem_alloc(tmem_slot, L::TMEM_COLS);
+    tmem_relinquish();
   }
   tc_fence_before();
-  if constexpr (PAIR) {  // the peer's barriers must be initialised before anything is signalled on them
-    cluster_arrive();
-    cluster_wait();
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();  // everything above overlapped the previous kernel's tail; from here on we read its results
@@ -173,7 +150,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t lead_full = PAIR ? mapa_shared(smem_u32(&full[0]), 0) : 0u;  // leader's full[] barriers
       if constexpr (WS) {
         // gridDim.x is a multiple of tiles_n, so t % tiles_n is the same for every tile of this CTA
         const int n_tile_fixed = static_cast<int>(blockIdx.x) % p.tiles_n;
@@ -182,13 +158,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_load_2d(b_res + kb * L::B_BYTES, &mapB, b_full, kb * BK, n_tile_fixed * BN);
       }
       for (int t = unit; t < p.tiles_total; t += n_units) {
-        const int tile = SPLIT ? t / p.splits : t;
-        const int ks = SPLIT ? t - tile * p.splits : 0;
-        [[maybe_unused]] const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
-        [[maybe_unused]] const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
-        [[maybe_unused]] int kb = 0;
-        const int n_tile = tile % p.tiles_n;
-        int m_tile = (tile / p.tiles_n) * CTAS + static_cast<int>(rank);
+        const int n_tile = t % p.tiles_n;
+        int m_tile = t / p.tiles_n;
         const int x0 = (m_tile % p.tiles_x) * p.TW;
         m_tile /= p.tiles_x;
         const int y0 = (m_tile % p.tiles_y) * p.TH;
@@ -197,30 +168,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           const int ky = (p.ntaps == 9) ? tap / 3 : 1;
           const int kx = (p.ntaps == 9) ? tap % 3 : 1;
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
-            if constexpr (SPLIT) {  // only the k-blocks of this work item's slice
-              const int cur = kb++;
-              if (cur < kb0 || cur >= kb1) continue;
-            }
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + L::A_BYTES;
-            if constexpr (PAIR) {
-              // both CTAs' bytes are counted on the leader's barrier (the peer's stage was released by the same
-              // multicast commit as the leader's, so it cannot run a whole phase ahead of the leader's expect_tx)
-              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * L::STAGE_BYTES);
-              const uint32_t fb = lead_full + stage * 8;
-              if constexpr (S2) {
-                const int px = (kx == 1) ? 0 : 1, py = (ky == 1) ? 0 : 1;
-                const int wx = x0 + ((kx == 0) ? -1 : 0), hy = y0 + ((ky == 0) ? -1 : 0);
-                tma_load_5d_pair(sa, &mapA, fb, px * p.c_s2 + kc * BK, wx, py, hy, n0);
-              } else {
-                if (kc < p.kc_a1)
-                  tma_load_4d_pair(sa, &mapA, fb, kc * BK, x0 + kx - 1, y0 + ky - 1, n0);
-                else
-                  tma_load_4d_pair(sa, &mapA2, fb, (kc - p.kc_a1) * BK, x0 + kx - 1, y0 + ky - 1, n0);
-              }
-              tma_load_2d_pair(sb, &mapB, fb, tap * p.cin + kc * BK, n_tile * BN + static_cast<int>(rank) * (BN / 2));
-            } else if constexpr (WS) {
+            if constexpr (WS) {
               mbar_arrive_expect_tx(&full[stage], L::A_BYTES);
               tma_load_4d(sa, &mapA, &full[stage], kc * BK, x0 + kx - 1, y0 + ky - 1, n0);
             } else {
@@ -246,11 +197,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && leader) {
-    // ===================== MMA issuer (of a pair: the leader CTA only) =====================
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
     // Warp-uniform control flow: all lanes wait on the barriers and build the descriptors (uniform registers),
     // one elected lane issues the tcgen05.mma / commit instructions.
-    constexpr uint32_t idesc = umma_idesc_bf16(BM * CTAS, BN);
+    constexpr uint32_t idesc = umma_idesc_bf16(BM, BN);
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_base = __shfl_sync(0xffffffffu, smem_u32(smem), 0);
     int stage = 0;
@@ -266,10 +217,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tb + acc * L::ACC_STRIDE;
-      const int ks = SPLIT ? t % p.splits : 0;
-      const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
-      const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
-      for (int kb = kb0; kb < kb1; ++kb) {
+      for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
@@ -278,17 +226,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                   : umma_desc_sw128(sa + L::A_BYTES);
         if (elect_one()) {
           // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
-          if constexpr (PAIR) {
-            umma_ss_pair(d_tmem, adesc, bdesc, idesc, kb != kb0);
+          umma_ss(d_tmem, adesc, bdesc, idesc, kb != 0);
 #pragma unroll
-            for (int k = 1; k < BK / 16; ++k) umma_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
-            umma_commit_pair(&empty[stage], 3);  // frees the stage in both CTAs
-          } else {
-            umma_ss(d_tmem, adesc, bdesc, idesc, kb != kb0);
-#pragma unroll
-            for (int k = 1; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
-            umma_commit(&empty[stage]);
-          }
+          for (int k = 1; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
+          umma_commit(&empty[stage]);
         }
         __syncwarp();
         if (++stage == L::STAGES) {
@@ -296,12 +237,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           phase ^= 1;
         }
       }
-      if (elect_one()) {
-        if constexpr (PAIR)
-          umma_commit_pair(&tmem_full[acc], 3);  // both CTAs' epilogues drain their half of the accumulator
-        else
-          umma_commit(&tmem_full[acc]);
-      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
       __syncwarp();
     }
   } else if (warp >= 2) {
@@ -325,11 +261,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
     uint32_t g = 0;  // running chunk counter -> staging buffer + barrier parity
     int it = wg;     // index of the tile in this CTA's sequence: stage it & 1 == wg
-    const uint32_t lead_tmem_empty = PAIR ? mapa_shared(smem_u32(&tmem_empty[0]), 0) : 0u;
     for (int t = unit + wg * n_units; t < p.tiles_total; t += 2 * n_units, it += 2) {
-      const int tile = SPLIT ? t / p.splits : t;
-      const int n_tile = tile % p.tiles_n;
-      int m_tile = (tile / p.tiles_n) * CTAS + static_cast<int>(rank);
+      const int n_tile = t % p.tiles_n;
+      int m_tile = t / p.tiles_n;
       const int x0 = (m_tile % p.tiles_x) * p.TW;
       m_tile /= p.tiles_x;
       const int y0 = (m_tile % p.tiles_y) * p.TH;
@@ -338,39 +272,6 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int col_base = n_tile * out_cols_per_tile;
-
-      [[maybe_unused]] const float* part_rd = nullptr;
-      if constexpr (SPLIT) {
-        // publish this k-slice's fp32 partial rows, hand the accumulator back, take a ticket for the 32-row slab
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-        const uint32_t t_part = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
-        const int ks = t - tile * p.splits;
-        float* part = p.ws_partial + (static_cast<size_t>(tile) * p.splits + ks) * (BM * BN) +
-                      static_cast<size_t>(row) * BN;
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t r[32];
-          tmem_ld_32x32b_x32(t_part + c * 32, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<uint4*>(part + c * 32 + j * 4) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        }
-        tc_fence_before();
-        __threadfence();  // partial rows visible device-wide before the ticket is taken
-        __syncwarp();
-        int last = 0;
-        if (lane == 0) {
-          mbar_arrive(&tmem_empty[acc]);
-          unsigned int* tk = p.ws_tickets + tile * 4 + q;
-          last = atomicAdd(tk, 1u) == static_cast<unsigned int>(p.splits - 1);
-          if (last) *tk = 0u;  // re-arm for the next launch
-        }
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (!last) continue;
-        __threadfence();
-        part_rd = p.ws_partial + static_cast<size_t>(tile) * p.splits * (BM * BN) + static_cast<size_t>(row) * BN;
-      }
 
       // prefetch residual slabs for the first two chunks (their buffers are free: at most one store
       // group from the previous tile may still be reading, and it is neither of these two buffers
@@ -387,10 +288,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
       }
 
-      if constexpr (!SPLIT) {
-        mbar_wait(&tmem_full[acc], acc_phase);
-        tc_fence_after();
-      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
       const uint32_t t_acc = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
       int img = ln + n0 + (x0 + lx) / p.rows_per_img;
       img = img < p.img_max ? img : p.img_max;
@@ -419,19 +318,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         float v[32];
         if (!p.geglu) {
-          if constexpr (SPLIT) {
-            // slices in slice order (fixed summation order whichever CTA arrived last); L2-coherent loads
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            for (int sl = 0; sl < p.splits; ++sl) {
-              const float4* src = reinterpret_cast<const float4*>(part_rd + static_cast<size_t>(sl) * (BM * BN) + c * 32);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 f = __ldcg(src + j);
-                v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
-              }
-            }
-          } else {
+          {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_acc + c * 32, r);
             tmem_ld_wait();
@@ -521,33 +408,20 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_store_commit();
         }
       }
-      // accumulator fully read -> hand the TMEM stage back to the MMA warp (SPLIT: already done above)
+      // accumulator fully read -> hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (!SPLIT && lane == 0) {
-        if (PAIR && !leader)
-          mbar_arrive_cluster(lead_tmem_empty + acc * 8);  // the MMA issuer waits on the leader's barrier
-        else
-          mbar_arrive(&tmem_empty[acc]);
-      }
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if (lane == 0) tma_store_wait_all0();
   }
 
   tc_fence_before();
-  if constexpr (PAIR) {  // no CTA may exit (or free TMEM) while its peer's MMAs / remote arrivals are in flight
-    cluster_arrive();
-    cluster_wait();
-  } else {
-    __syncthreads();
-  }
+  __syncthreads();
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    if constexpr (PAIR)
-      tmem_dealloc_pair(tmem_base, L::TMEM_COLS);
-    else
-      tmem_dealloc(tmem_base, L::TMEM_COLS);
+    tmem_dealloc(tmem_base, L::TMEM_COLS);
   }
 }
 
@@ -582,108 +456,26 @@ static void pick_tile(int Nimg, int H, int W, int* TW, int* TH, int* TN) {
   (void)Nimg;
 }
 
-// CTA-pair (cta_group::2) tiles: EXPERIMENTAL, off unless MVD_GEMM_2CTA=1 — written against the L2<->SM traffic
-// ceiling measured in profiles/r1_tma_bw.txt, not yet run on hardware.
-static bool pair_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("MVD_GEMM_2CTA");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-
-// Weight-stationary tiles for K <= 320 linears: EXPERIMENTAL, off unless MVD_GEMM_WS=1 — not yet run on hardware.
+// Weight-stationary tiles for the K <= 320 linears whose N is a multiple of 128 (measured in round 2: q,k,v,q_ref at
+// M = 32768 38.5 -> 36.1 us, step 13.26 -> 13.08 ms). MVD_GEMM_WS=0 switches them off for A/B runs.
 static bool ws_enabled() {
   static const bool on = [] {
     const char* e = getenv("MVD_GEMM_WS");
-    return e != nullptr && e[0] == '1';
+    return e == nullptr || e[0] != '0';
   }();
   return on;
 }
 
-// Split-K: EXPERIMENTAL, off unless MVD_GEMM_SPLITK=1 and the caller registered a workspace
-// (mvd_gemm_set_workspace) — not yet run on hardware.
-static bool splitk_enabled() {
-  static const bool on = [] {
-    const char* e = getenv("MVD_GEMM_SPLITK");
-    return e != nullptr && e[0] == '1';
-  }();
-  return on;
-}
-static thread_local void* t_gemm_ws = nullptr;  // caller-owned, zero-filled once; see mvd_gemm_set_workspace
-static thread_local int64_t t_gemm_ws_bytes = 0;
-constexpr int64_t SPLITK_TICKET_BYTES = 4096 * sizeof(unsigned int);
-
-// Cost of one CTA's work in 128-byte rows moved between L2 and the SM (the measured bound of these kernels):
-// operand rows of its k-slice + the fp32 fix-up traffic of the last arriver (write 4*bn rows, read splits * 4*bn).
-static double splitk_cost(int bn, int k_blocks, int splits) {
-  const int kb = (k_blocks + splits - 1) / splits;
-  return static_cast<double>(128 + bn) * kb + (splits > 1 ? 4.0 * bn * (splits + 1) : 0.0);
-}
-
-// Picks (bn, splits) for an under-filled launch, or splits = 1. tiles_m: 128-row tiles.
-static void pick_splitk(int N, int tiles_m, int k_blocks, int single_bn, int* bn_out, int* splits_out) {
-  *bn_out = single_bn;
-  *splits_out = 1;
-  const int sms = sm_count();
-  const long tiles1 = static_cast<long>((N + single_bn - 1) / single_bn) * tiles_m;
-  if (!splitk_enabled() || t_gemm_ws == nullptr || tiles1 > sms) return;  // more than one wave: leave it alone
-  double best = splitk_cost(single_bn, k_blocks, 1) * 0.8;  // a split must promise >= 20 %
-  const int cands[] = {160, 128, 64};
-  for (int bn : cands) {
-    const long tiles = static_cast<long>((N + bn - 1) / bn) * tiles_m;
-    if (tiles > 1024) continue;  // ticket table: 4 counters per tile
-    for (int sp = 2; sp <= 8; ++sp) {
-      if (tiles * sp > sms || k_blocks / sp < 4) break;
-      const int64_t need = SPLITK_TICKET_BYTES + static_cast<int64_t>(tiles) * sp * BM * bn * 4;
-      if (need > t_gemm_ws_bytes) break;
-      const double c = splitk_cost(bn, k_blocks, sp);
-      if (c < best) {
-        best = c;
-        *bn_out = bn;
-        *splits_out = sp;
-      }
-    }
-  }
-}
-
-template <int BN, bool S2, int CTAS>
+template <int BN, bool S2>
 static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
                       const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
-  using L = SmemLayout<BN, CTAS>;
-  static bool configured = false;  // benign race: attribute set is idempotent
-  if (!configured) {
-    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, S2, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  L::TOTAL));
-    configured = true;
-  }
-  int units = sm_count() / CTAS;  // CTAs, or CTA pairs (one CTA per SM)
+  using L = SmemLayout<BN>;
+  // per call: cheap, and correct for every device a process may touch
+  MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, S2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+  int units = sm_count();  // one CTA per SM
   if (args.tiles_total < units) units = args.tiles_total;
-  if constexpr (CTAS == 1) {
-    MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, S2, 1>, dim3(units), dim3(GEMM_THREADS), L::TOTAL, stream, mA, mA2, mB,
-                        mO, mR, args));
-  } else {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(units * CTAS);
-    cfg.blockDim = dim3(GEMM_THREADS);
-    cfg.dynamicSmemBytes = L::TOTAL;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CTAS;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    int na = 1;
-    if (pdl_enabled()) {
-      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[na].val.programmaticStreamSerializationAllowed = 1;
-      ++na;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    MVD_CUDA(cudaLaunchKernelEx(&cfg, gemm_conv_kernel<BN, S2, CTAS>, mA, mA2, mB, mO, mR, args));
-  }
+  MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, S2>, dim3(units), dim3(GEMM_THREADS), L::TOTAL, stream, mA, mA2, mB, mO, mR,
+                      args));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -691,37 +483,15 @@ static int launch_one(const CUtensorMap& mA, const CUtensorMap& mA2, const CUten
 
 static int launch_ws(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
                      const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
-  using L = SmemLayout<128, 1, true>;
-  static bool configured = false;
-  if (!configured) {
-    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<128, false, 1, false, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    configured = true;
-  }
+  using L = SmemLayout<128, true>;
+  MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<128, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                L::TOTAL));
   // every CTA keeps one column tile: grid = tiles_n * (row groups that fit on the machine)
   const int tiles_m = args.tiles_total / args.tiles_n;
   int groups = sm_count() / args.tiles_n;
   if (groups > tiles_m) groups = tiles_m;
-  MVD_CUDA(launch_pdl(gemm_conv_kernel<128, false, 1, false, true>, dim3(groups * args.tiles_n), dim3(GEMM_THREADS),
-                      L::TOTAL, stream, mA, mA2, mB, mO, mR, args));
-  MVD_CUDA(cudaGetLastError());
-  count_launches(1);
-  return MVD_OK;
-}
-
-template <int BN>
-static int launch_split(const CUtensorMap& mA, const CUtensorMap& mA2, const CUtensorMap& mB, const CUtensorMap& mO,
-                        const CUtensorMap& mR, const GemmArgs& args, cudaStream_t stream) {
-  using L = SmemLayout<BN, 1>;
-  static bool configured = false;
-  if (!configured) {
-    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<BN, false, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  L::TOTAL));
-    configured = true;
-  }
-  const int grid = args.tiles_total < sm_count() ? args.tiles_total : sm_count();
-  MVD_CUDA(launch_pdl(gemm_conv_kernel<BN, false, 1, true>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream, mA, mA2,
-                      mB, mO, mR, args));
+  MVD_CUDA(launch_pdl(gemm_conv_kernel<128, false, true>, dim3(groups * args.tiles_n), dim3(GEMM_THREADS), L::TOTAL,
+                      stream, mA, mA2, mB, mO, mR, args));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;
@@ -753,23 +523,10 @@ static int pick_bn(int N, int M_tiles, bool geglu) {
   return best;
 }
 
-// Tile width of a CTA-pair launch (256 x BN tiles over sm_count()/2 pairs), or 0 when pairs are off / not worthwhile:
-// a pair tile costs about what a single-CTA tile of the same width costs, so the two cost figures compare directly.
-static int pick_bn_pair(int N, int M_tiles, int force_bn, int single_bn) {
-  if (!pair_enabled() || M_tiles < 2) return 0;
-  const int m_pairs = (M_tiles + 1) / 2;
-  const int units = sm_count() / 2;
-  if (force_bn > 0) return (force_bn == 256 || force_bn == 160) ? force_bn : 0;
-  const double c160 = bn_cost(N, m_pairs, 160, units), c256 = bn_cost(N, m_pairs, 256, units);
-  const int bn = c256 <= c160 ? 256 : 160;
-  const double single = bn_cost(N, M_tiles, single_bn, sm_count());
-  return (c256 <= c160 ? c256 : c160) <= 1.15 * single ? bn : 0;  // operand traffic per FLOP is ~1.6x lower
-}
-
-// The scheduling decision for one problem: tile width, CTAs per tile (2 = CTA pair), k-slices.
+// The scheduling decision for one problem: pixel tile shape, tile width, weight-stationary or streaming.
 struct GemmPlan {
   int TW, TH, TN, tiles_m;
-  int bn, ctas, splits;
+  int bn;
   bool ws;  // weight-stationary 128-wide tiles (grid must then be a multiple of the column-tile count)
 };
 static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, int stride, int geglu, int force_bn,
@@ -778,21 +535,12 @@ static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, 
   pick_tile(Nimg, H, W, &pl.TW, &pl.TH, &pl.TN);
   pl.tiles_m = ((W + pl.TW - 1) / pl.TW) * ((H + pl.TH - 1) / pl.TH) * ((Nimg + pl.TN - 1) / pl.TN);
   pl.bn = force_bn > 0 ? force_bn : pick_bn(Cout, pl.tiles_m, geglu != 0);
-  const int pair_bn = pick_bn_pair(Cout, pl.tiles_m, force_bn, pl.bn);
-  pl.ctas = pair_bn > 0 ? 2 : 1;
-  if (pair_bn > 0) pl.bn = pair_bn;
-  pl.splits = 1;
   // weight-stationary: 1-tap, K <= 320, N a multiple of 128 (GEGLU: only with the 128-wide interleave), enough row
   // tiles that every CTA amortises its resident weight tile over several of them
-  pl.ws = ws_enabled() && pl.ctas == 1 && ntaps == 1 && stride == 1 && Cin <= WS_MAX_KBLOCKS * BK &&
-          Cout % 128 == 0 && (force_bn == 0 || force_bn == 128) && (!geglu || force_bn == 128) &&
-          !two_source && Cout / 128 <= sm_count() && pl.tiles_m * (Cout / 128) >= 4 * sm_count();
+  pl.ws = ws_enabled() && ntaps == 1 && stride == 1 && Cin <= WS_MAX_KBLOCKS * BK && Cout % 128 == 0 &&
+          (force_bn == 0 || force_bn == 128) && (!geglu || force_bn == 128) && !two_source &&
+          Cout / 128 <= sm_count() && pl.tiles_m * (Cout / 128) >= 4 * sm_count();
   if (pl.ws) pl.bn = 128;
-  if (!pl.ws && pl.ctas == 1 && force_bn == 0 && !geglu && stride == 1) {
-    int bn_split = pl.bn;
-    pick_splitk(Cout, pl.tiles_m, ntaps * (Cin / 64), pl.bn, &bn_split, &pl.splits);
-    if (pl.splits > 1) pl.bn = bn_split;
-  }
   return pl;
 }
 
@@ -849,15 +597,9 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   g.img_max = rows_per_img > 0 ? (W - 1) / rows_per_img : Nimg - 1;
   g.bias = static_cast<const __nv_bfloat16*>(bias);
 
-  const int BN = pl.bn, ctas = pl.ctas, splits = pl.splits;
+  const int BN = pl.bn;
   g.tiles_n = (Cout + BN - 1) / BN;
-  g.tiles_total = g.tiles_n * ((tiles_m + ctas - 1) / ctas);  // scheduling units: tiles, or 256-row pair tiles
-  g.splits = splits;
-  if (splits > 1) {
-    g.ws_tickets = static_cast<unsigned int*>(t_gemm_ws);
-    g.ws_partial = reinterpret_cast<float*>(static_cast<char*>(t_gemm_ws) + SPLITK_TICKET_BYTES);
-    g.tiles_total *= splits;  // work items: (tile, k-slice), slice fastest
-  }
+  g.tiles_total = g.tiles_n * tiles_m;
 
   CUtensorMap mA, mA2, mB, mO, mR;
   // --- A maps
@@ -894,7 +636,7 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   {
     const uint64_t dims[2] = {static_cast<uint64_t>(ntaps) * Cin, static_cast<uint64_t>(Cout)};
     const uint64_t strides[1] = {static_cast<uint64_t>(ldw) * 2};
-    const uint32_t box[2] = {64, static_cast<uint32_t>(BN / ctas)};  // a CTA of a pair loads its half of the tile
+    const uint32_t box[2] = {64, static_cast<uint32_t>(BN)};
     if (int e = make_tmap_bf16(&mB, w, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
   }
   // --- output / residual maps (per-warp slab boxes of 32 pixels x 32 channels, 64-B swizzle)
@@ -921,24 +663,10 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   }
 
   if (pl.ws) return launch_ws(mA, mA2, mB, mO, mR, g, stream);
-  if (splits > 1) {
-    switch (BN) {
-      case 64: return launch_split<64>(mA, mA2, mB, mO, mR, g, stream);
-      case 128: return launch_split<128>(mA, mA2, mB, mO, mR, g, stream);
-      default: return launch_split<160>(mA, mA2, mB, mO, mR, g, stream);
-    }
-  }
-  if (ctas == 2) {
-    if (BN == 256)
-      return stride == 2 ? launch_one<256, true, 2>(mA, mA2, mB, mO, mR, g, stream)
-                         : launch_one<256, false, 2>(mA, mA2, mB, mO, mR, g, stream);
-    return stride == 2 ? launch_one<160, true, 2>(mA, mA2, mB, mO, mR, g, stream)
-                       : launch_one<160, false, 2>(mA, mA2, mB, mO, mR, g, stream);
-  }
 #define MVD_LAUNCH_BN(bn)                                                               \
   case bn:                                                                              \
-    return stride == 2 ? launch_one<bn, true, 1>(mA, mA2, mB, mO, mR, g, stream)        \
-                       : launch_one<bn, false, 1>(mA, mA2, mB, mO, mR, g, stream);
+    return stride == 2 ? launch_one<bn, true>(mA, mA2, mB, mO, mR, g, stream)           \
+                       : launch_one<bn, false>(mA, mA2, mB, mO, mR, g, stream);
   switch (BN) {
     MVD_LAUNCH_BN(64)
     MVD_LAUNCH_BN(128)
@@ -956,35 +684,23 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
 extern "C" {
 
 int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntaps, int stride, int geglu, int tile_n,
-                  int* bn, int* ctas, int* splits, int* grid) {
+                  int* bn, int* weight_stationary, int* grid) {
   using namespace mvd;
   MVD_CHECK(n_img > 0 && h_out > 0 && w_out > 0 && c_in > 0 && c_in % 64 == 0 && c_out > 0 && c_out % 32 == 0 &&
                 (ntaps == 1 || ntaps == 9) && (stride == 1 || stride == 2),
             "gemm_plan: unsupported problem");
   const GemmPlan pl = plan_gemm(n_img, h_out, w_out, c_in, c_out, ntaps, stride, geglu, tile_n, false);
-  const int units = ((c_out + pl.bn - 1) / pl.bn) * ((pl.tiles_m + pl.ctas - 1) / pl.ctas) * pl.splits;
-  const int cap = sm_count() / pl.ctas;
+  const int units = ((c_out + pl.bn - 1) / pl.bn) * pl.tiles_m;
   if (bn) *bn = pl.bn;
-  if (ctas) *ctas = pl.ctas;
-  if (splits) *splits = pl.splits;
+  if (weight_stationary) *weight_stationary = pl.ws ? 1 : 0;
   if (grid) {
-    *grid = (units < cap ? units : cap) * pl.ctas;
+    *grid = units < sm_count() ? units : sm_count();
     if (pl.ws) {
       const int tn = c_out / 128;
       const int groups = sm_count() / tn < pl.tiles_m ? sm_count() / tn : pl.tiles_m;
       *grid = groups * tn;
     }
   }
-  return MVD_OK;
-}
-
-int mvd_gemm_set_workspace(void* workspace, int64_t bytes) {
-  using namespace mvd;
-  MVD_CHECK(workspace == nullptr || ((reinterpret_cast<uintptr_t>(workspace) & 15) == 0 && bytes > SPLITK_TICKET_BYTES),
-            "gemm workspace must be 16-byte aligned and larger than %lld bytes",
-            static_cast<long long>(SPLITK_TICKET_BYTES));
-  t_gemm_ws = workspace;
-  t_gemm_ws_bytes = workspace ? bytes : 0;
   return MVD_OK;
 }
 

@@ -86,7 +86,6 @@ def linear(
         pg, ldg, _, Ng = _rows2d(row_group_bias, "row_group_bias")
         if Ng != N or rows_per_group <= 0:
             raise ValueError("row_group_bias must be [groups, N] with rows_per_group > 0")
-    _register_gemm_workspace(a.device)
     check(
         lib().mvd_linear_bf16(pa, lda, k1, pa2, lda2, k2, pw, ldw, _p(bias), pg, ldg, rows_per_group, pr, ldr, po, ldo,
                               M, N, int(geglu), tile_n, _stream()),
@@ -140,7 +139,6 @@ def conv3x3(
         _req(img_bias, "img_bias", torch.float32)
         if tuple(img_bias.shape) != (n, cout) or img_bias.stride(1) != 1:
             raise ValueError("img_bias must be fp32 [N, Cout] with unit inner stride")
-    _register_gemm_workspace(x.device)
     check(
         lib().mvd_conv3x3_bf16(_p(x), c1, _p(x2), c2, _p(w), _p(bias), _p(img_bias),
                                0 if img_bias is None else img_bias.stride(0), _p(residual), _p(out), n, ho, wo,
@@ -182,18 +180,6 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
 # ----------------------------------------------------------------------------------------------------------
 F32 = torch.float32
 _workspaces: dict = {}
-
-
-_SPLITK = os.environ.get("MVD_GEMM_SPLITK", "0") == "1"  # experimental split-K GEMMs (csrc/gemm.cu), off by default
-_GEMM_WS_FLOATS = 4 << 20  # 16 MiB: tickets + 148 fp32 partial tiles of 128 x 160
-
-
-def _register_gemm_workspace(device) -> None:
-    """Hands the calling thread's GEMM launches a per-(device, stream) scratch buffer (mvd_gemm_set_workspace)."""
-    if not _SPLITK:
-        return
-    ws = _workspace(device, _GEMM_WS_FLOATS, "gemm")
-    check(lib().mvd_gemm_set_workspace(ws.data_ptr(), ws.numel() * 4), "mvd_gemm_set_workspace")
 
 
 def _workspace(device, nfloats: int, tag: str = "ws") -> torch.Tensor:

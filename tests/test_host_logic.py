@@ -88,10 +88,9 @@ import ctypes, json
 from mvd_b200._lib import lib
 L = lib()
 def plan(n, h, w, cin, cout, taps=1, stride=1, geglu=0, tile=0):
-    o = [ctypes.c_int() for _ in range(4)]
+    o = [ctypes.c_int() for _ in range(3)]
     assert L.mvd_gemm_plan(n, h, w, cin, cout, taps, stride, geglu, tile, *[ctypes.byref(x) for x in o]) == 0
     return [x.value for x in o]
-assert L.mvd_gemm_set_workspace(ctypes.c_void_p(0x10000), 16 << 20) == 0   # planning only: never dereferenced
 print(json.dumps({
     "qkv64": plan(1, 1, 32768, 320, 1280), "proj64": plan(1, 1, 32768, 320, 320),
     "geglu64": plan(1, 1, 32768, 320, 2560, geglu=1, tile=256), "conv64": plan(8, 64, 64, 320, 320, 9),
@@ -112,28 +111,19 @@ def _plans(env_extra):
     return json.loads(out.stdout.strip().splitlines()[-1])
 
 
-def test_gemm_plan_default_is_single_cta_unsplit():
-    """[bn, ctas, splits, grid]: by default no launch uses CTA pairs or split-K (both are opt-in, unmeasured)."""
+def test_gemm_plan_defaults():
+    """[bn, weight_stationary, grid] of the planner for the step's shape classes (round-2 measured defaults)."""
     p = _plans({})
-    assert all(v[1] == 1 and v[2] == 1 for v in p.values()), p
-    assert p["proj64"][0] == 160 and p["conv64"][0] == 160 and p["conv64"][3] == 148
-    assert p["geglu64"][0] == 256                     # GEGLU tile width is dictated by the weight interleave
-    assert p["conv8"] == [64, 1, 1, 80]               # 4 row tiles x 20 column tiles: the under-filled case
+    assert p["qkv64"] == [128, 1, 140]                # 10 column tiles x 14 row groups: every CTA keeps one weight tile
+    assert p["proj64"][:2] == [160, 0] and p["conv64"] == [160, 0, 148]   # N = 320 is not a multiple of 128
+    assert p["geglu64"][:2] == [256, 0]               # GEGLU tile width is dictated by the weight interleave
+    assert p["conv8"] == [64, 0, 80]                  # 4 row tiles x 20 column tiles: the under-filled case
+    assert p["ff2_8"] == [64, 0, 80] and p["down8"][1] == 0
 
 
-def test_gemm_plan_pair_and_splitk_flags():
-    pair = _plans({"MVD_GEMM_2CTA": "1"})
-    assert pair["qkv64"][:3] == [256, 2, 1] and pair["conv64"][:3] == [160, 2, 1]
-    assert pair["conv64"][3] % 2 == 0 and pair["conv64"][3] <= 148
-    assert pair["conv8"][1] == 1                      # 4 row tiles: pairs would only halve the parallelism
-    split = _plans({"MVD_GEMM_SPLITK": "1"})
-    assert split["conv8"][1] == 1 and split["conv8"][2] >= 2 and split["conv8"][3] <= 148
-    assert split["ff2_8"][2] >= 2
-    assert split["qkv64"][2] == 1 and split["down8"][2] == 1   # full launches and stride-2 convs stay un-split
-    ws = _plans({"MVD_GEMM_WS": "1"})
-    assert ws["qkv64"] == [128, 1, 1, 140]            # 10 column tiles x 14 row groups: every CTA keeps one weight tile
-    assert ws["proj64"][0] == 160 and ws["geglu64"][0] == 256   # N = 320 and the 256-wide GEGLU interleave stay as they are
-    assert ws["conv64"][0] == 160 and ws["ff2_8"] == [64, 1, 1, 80]
+def test_gemm_plan_weight_stationary_switch():
+    off = _plans({"MVD_GEMM_WS": "0"})
+    assert all(v[1] == 0 for v in off.values()), off
 
 
 def test_product_scheduler_reproduces_reference_goldens():
