@@ -80,6 +80,19 @@ int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_stride, const
                        int64_t ldo, int64_t o_batch_stride, int batch, int heads, int s_q, int s_kv, float scale,
                        void* stream);
 
+/* Same operator with a caller-owned scratch buffer of mvd_attention_workspace_bytes() bytes (16-byte aligned,
+ * zero-filled once, private to launches that cannot run concurrently, e.g. one per stream). With it, the units of a
+ * launch's last partial wave are split along S_kv over the idle SMs and merged by whichever CTA finishes a unit last
+ * (deterministic part order); without it (NULL) every (256-row tile pair, head, batch) unit runs on one CTA.
+ * k_batch_stride = v_batch_stride = 0 shares one K/V sequence between all batch entries: the cross-view reference
+ * mode of configs[3], where every view attends over the concatenated tokens of all views
+ * (src/models/attention.py:190-197 accepts a 3-D reference; :126-132 projects it once). */
+int64_t mvd_attention_workspace_bytes(void);
+int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch_stride, const void* k, int64_t ldk,
+                          int64_t k_batch_stride, const void* v, int64_t ldv, int64_t v_batch_stride, void* out,
+                          int64_t ldo, int64_t o_batch_stride, int batch, int heads, int s_q, int s_kv, float scale,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Bandwidth-bound normalisation kernels, csrc/norm.cu
  * ------------------------------------------------------------------------------------------------------- */

@@ -150,7 +150,9 @@ def conv3x3(
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """q: [B,Sq,>=heads*64] view, k/v: [B,Skv,...] views (unit inner stride); head h = columns h*64.. ."""
+    """q: [B,Sq,>=heads*64] view, k/v: [B,Skv,...] views (unit inner stride); head h = columns h*64.. .
+    k/v may be batch-broadcast views (stride(0) == 0, e.g. `kv.expand(B, -1, -1)`): one K/V sequence shared by all
+    batch entries (cross-view reference mode)."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, nme)
         if t.dim() != 3 or t.stride(2) != 1 or t.shape[2] != heads * 64:
@@ -166,13 +168,26 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
         raise ValueError("out must be [B,Sq,heads*64] with unit inner stride")
     if scale is None:
         scale = 0.125
+    nbytes = _attn_ws_bytes()
+    ws = _workspace(q.device, nbytes // 4, "attn")  # per (device, stream): the two adapter branches never share one
     check(
-        lib().mvd_attention_bf16(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
-                                 v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1), out.stride(0),
-                                 B, heads, Sq, Skv, float(scale), _stream()),
-        "mvd_attention_bf16",
+        lib().mvd_attention_bf16_ws(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
+                                    v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1),
+                                    out.stride(0), B, heads, Sq, Skv, float(scale), ws.data_ptr(), ws.numel() * 4,
+                                    _stream()),
+        "mvd_attention_bf16_ws",
     )
     return out
+
+
+_ATTN_WS_BYTES = None
+
+
+def _attn_ws_bytes() -> int:
+    global _ATTN_WS_BYTES
+    if _ATTN_WS_BYTES is None:
+        _ATTN_WS_BYTES = int(lib().mvd_attention_workspace_bytes())
+    return _ATTN_WS_BYTES
 
 
 # ----------------------------------------------------------------------------------------------------------

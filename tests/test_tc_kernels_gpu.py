@@ -160,6 +160,43 @@ def test_attention(B, heads, Sq, Skv, qscale):
     _cmp(out, _attn_ref(q, k, v, heads, 0.125), f"attn B{B} h{heads} {Sq}x{Skv} qs{qscale}", atol=1.5e-2)
 
 
+@pytest.mark.parametrize("B,heads,Sq,Skv", [(2, 5, 4096, 4096),     # 160 units on 148 SMs: 12 tail units x 8 KV parts
+                                             (8, 5, 4096, 4096),     # 640 units: 48 tail units x 3 parts
+                                             (3, 5, 4000, 1000 + 8),  # ragged rows and a masked last KV block in a part
+                                             (1, 10, 4096, 2048),    # 160 units, 16 KV blocks: 4 parts
+                                             (2, 10, 2304, 2304)])   # 96^2 latent level-1 site of a view-sharded rank
+def test_attention_kv_split_tail(B, heads, Sq, Skv, monkeypatch):
+    """The last partial wave is split along S_kv and merged by the last-arriving CTA: same result as the un-split
+    launch (MVD_ATTN_SPLIT=0 is read once per process, so the comparison is against fp32 SDPA), bit-identical
+    across repeated launches (fixed merge order), ticket counters re-armed."""
+    from mvd_b200 import ops
+
+    C = heads * 64
+    q = _randn(B, Sq, C, scale=2.0, seed=1)
+    k = _randn(B, Skv, C, seed=2)
+    v = _randn(B, Skv, C, seed=3)
+    outs = [ops.attention(q, k, v, heads).clone() for _ in range(3)]
+    torch.cuda.synchronize()
+    _cmp(outs[0], _attn_ref(q, k, v, heads, 0.125), f"attn split B{B} h{heads} {Sq}x{Skv}", atol=1.5e-2)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_attention_shared_kv_batch_broadcast():
+    """k/v with batch stride 0 (one reference sequence for every view, configs[3] cross-view mode) == the same K/V
+    materialised per batch entry, bit for bit; both kernels (one-tile and two-tile)."""
+    from mvd_b200 import ops
+
+    for (B, heads, Sq, Skv) in [(4, 5, 256, 1024), (8, 5, 2304, 4 * 2304)]:
+        C = heads * 64
+        q = _randn(B, Sq, C, seed=1)
+        k1, v1 = _randn(1, Skv, C, seed=2), _randn(1, Skv, C, seed=3)
+        shared = ops.attention(q, k1.expand(B, -1, -1), v1.expand(B, -1, -1), heads)
+        full = ops.attention(q, k1.repeat(B, 1, 1), v1.repeat(B, 1, 1), heads)
+        torch.cuda.synchronize()
+        assert torch.equal(shared, full)
+        _cmp(shared, _attn_ref(q, k1.repeat(B, 1, 1), v1.repeat(B, 1, 1), heads, 0.125), "attn shared kv", atol=1.5e-2)
+
+
 def test_attention_strided_fused_qkv():
     """q/k/v as column slices of one fused projection output, out written into a slice of a wider buffer."""
     from mvd_b200 import ops
