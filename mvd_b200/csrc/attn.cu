@@ -296,9 +296,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant_
 // profiles/r2_softmax_pipe.txt): the two warps that share an SM sub-partition's MUFU settle in anti-phase by
 // themselves and the period of a KV block is the serial chain of ONE warp (S wait, TMEM load, row max, 128 MUFU.EX2
 // at 8 cycles each, P store). Strict MUFU hand-over between the two warps (per-sub-partition mbarriers), a one-sided
-// hand-over, four warps per sub-partition (column halves, row maximum agreed through shared memory) and a look-ahead
-// row maximum with split P publication were all built and timed: 273-306 us against 257 us for this free-running
-// form at the configs[1] top site. Packed fp32x2 instructions issue at half rate (no throughput gain over scalar,
+// hand-over, four warps per sub-partition (column halves, row maximum agreed through shared memory), a look-ahead
+// row maximum with split P publication and a two-half software pipeline of the block (TMEM load and row maximum of the
+// next half hidden behind the exponentials) were all built and timed: 264-306 us against 250-257 us for this
+// free-running form at the configs[1] top site; ncu: XU pipe 67 %, tensor pipe 33 % active (r2_attn_pair_ncu.txt). Packed fp32x2 instructions issue at half rate (no throughput gain over scalar,
 // only fewer issue slots), and a degree-3 FMA-pipe exp2 costs ~7.4 issue cycles per element against 8 MUFU cycles,
 // so the polynomial share (POLY8 eighths) buys little; it stays a template parameter.
 //
