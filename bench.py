@@ -12,11 +12,14 @@ processors), CFG combine + DDPM step. Reference-UNet features and their K/V are 
   value  : steps/s with everything resident in HBM; one captured CUDA graph replayed K times, CUDA events.
   e2e    : the same step through the public DenoiseSession API with HOST (pinned) latents + variance noise copied
            in and the updated latents copied out inside the timed region, every step.
-  N > 1  : `value` = sample-parallel weak scaling (configs[4]): every GPU denoises its own object, no data-path
-           collective; aggregate object-steps/s. "view_sharded" additionally reports strong scaling of ONE object
-           (configs[2]): views (N <= 4) or view x CFG branch (N = 8) sharded over ranks, reference features
-           normalised over the FULL batch on every rank; only per-step exchange = the CFG pair's prediction at N = 8
-           (NCCL all_gather of 128 KB).
+  N > 1  : `value` = STRONG scaling of ONE object (configs[2]): its 4 views x 2 CFG branches are sharded over the
+           ranks — views at N <= 4, view x CFG branch at N = 8 —, reference features normalised over the FULL batch on
+           every rank (attention.py:95-103 couples the batch); the only per-step exchange is the CFG pair's prediction
+           at N = 8 (NCCL all_gather of 128 KB inside the captured step). "sample_parallel" additionally reports the
+           zero-communication replica mode (configs[4]: one object per GPU, aggregate object-steps/s).
+  parity : (N = 1) the timed model — same weights — run on 2 views x 32^2 latents and compared with the fp32 CPU
+           oracle (north-star bound: normalised max-abs <= 2e-2, cosine >= 0.999), plus a finiteness check and checksum
+           of the latents the timed configuration produced.
 """
 from __future__ import annotations
 
@@ -37,6 +40,7 @@ import torch  # noqa: E402
 
 VIEWS, LATENT, CFG = 4, 64, 2
 WORKLOAD = ("configs[1]: one SD2.1 UNet + MV-adapter denoise step, 4 views at 512^2 (64^2 latent), CFG batch 2")
+METRIC = "MV denoise steps/s (SD2.1+adapter 512^2, 4 views x CFG 2)"
 GUIDANCE = 3.0
 INFER_STEPS = 50
 FLOPS_PER_STEP = 8.80e12  # 8 samples x 1151.6 GF minus the cached K/V projections
@@ -100,7 +104,8 @@ def build_pipeline(dev):
     return pipe
 
 
-def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch: int, use_graph=True, pipe=None):
+def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch: int, use_graph=True, pipe=None,
+                  sharded=None):
     """The slice of the object this rank owns: views [view0, view0+views_local), CFG branches
     (both if cfg_local == 2, else only `cfg_branch`: 0 = uncond, 1 = cond)."""
     from helpers import synthetic_inputs
@@ -115,7 +120,7 @@ def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch:
     # reference features are computed over ALL views on every rank (step-invariant; normalisation statistics
     # couple the batch, attention.py:95-103), this rank's processors then use the rows of its own samples
     unet.shard = None
-    if views_local < VIEWS:
+    if (views_local * cfg_local < VIEWS * CFG) if sharded is None else sharded:
         unet.shard = dict(view0=view0, views_local=views_local, views_total=VIEWS, cfg_total=CFG, cfg_branch=cfg_branch,
                           ie_text=inp["text"][VIEWS:].to(dev).contiguous())
     if cfg_local == 2:
@@ -164,42 +169,118 @@ def attention_roofline(dev, pk, how):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))["dram_bytes_per_launch"]
     except Exception:
         pass
-    return {"kernel": "attn_fwd2_kernel (B=8,h=5,Sq=Skv=4096,d=64)", "bound": "tensor", "achieved": round(achieved, 1),
+    return {"kernel": "attn_pair_kernel (B=8,h=5,Sq=Skv=4096,d=64)", "bound": "tensor", "achieved": round(achieved, 1),
             "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
             "peak_source": f"{how} burst bf16 GEMM", "ms_per_launch": round(ms, 4),
             "flops_per_launch": flops}
 
 
-def cpu_baseline(sample_views=2, latent=32, reps=2):
-    """Bounded CPU sample of the same path (oracle port of the reference's per-step work): full-width SD2.1 UNet +
-    adapters INCLUDING the frozen reference-UNet re-run the reference performs every step (mvd_unet.py:287), on
-    `sample_views` views at `latent`^2 latents, fp32, all host threads; scaled by algorithmic FLOPs to the
-    configs[1] step (4 views x CFG 2 at 64^2)."""
-    from flops import unet_flops
+_ORACLE = None
+
+
+def oracle_model(state_dict=None):
+    """The fp32 CPU oracle of MultiViewUNet at full SD2.1 width (test infrastructure: used here only as the checker
+    and as the CPU baseline). Built once; `state_dict` (the timed model's weights) is loaded when given."""
+    global _ORACLE
     from oracle.mv_adapter import MultiViewUNetOracle
+
+    if _ORACLE is None:
+        torch.manual_seed(0)
+        if state_dict is not None:
+            try:  # skip the random init of 1.8 G parameters: build on the meta device, adopt the given tensors
+                with torch.device("meta"):
+                    m = MultiViewUNetOracle(None, img_ref_scale=1.0, cam_modulation_strength=1.0, matched_batch_cfg=True)
+                m.load_state_dict({k: v.detach().float().cpu() for k, v in state_dict.items()}, assign=True)
+                state_dict = None
+            except Exception:
+                m = MultiViewUNetOracle(None, img_ref_scale=1.0, cam_modulation_strength=1.0, matched_batch_cfg=True)
+        else:
+            m = MultiViewUNetOracle(None, img_ref_scale=1.0, cam_modulation_strength=1.0, matched_batch_cfg=True)
+        _ORACLE = m.eval()
+    if state_dict is not None:
+        _ORACLE.load_state_dict({k: v.detach().float().cpu() for k, v in state_dict.items()})
+    return _ORACLE
+
+
+SAMPLE_VIEWS = 1  # the CPU arm times 1 of the 4 views (both CFG branches, full 64^2 latents, full-width model)
+
+
+def cpu_sample_step(m, inp):
+    """One bounded sample of the configs[1] step on the host: SAMPLE_VIEWS view(s) x CFG 2 at 64^2 latents through the
+    full-width oracle, INCLUDING the frozen reference-UNet re-run the reference performs every step (mvd_unet.py:287)."""
+    x = torch.cat([inp["latents"][:SAMPLE_VIEWS]] * CFG)
+    text = torch.cat([inp["text"][:VIEWS][:SAMPLE_VIEWS], inp["text"][VIEWS:][:SAMPLE_VIEWS]])
+    with torch.no_grad():
+        return m(x, 981, text, inp["source_camera"][:SAMPLE_VIEWS], inp["target_camera"][:SAMPLE_VIEWS],
+                 inp["source_latents"][:SAMPLE_VIEWS], pos_proj=inp["pos_proj"]).sample
+
+
+def cpu_baseline(reps=2, warmup=1, model=None):
+    """CPU baseline of the same metric: the oracle port of the reference's per-step work on the host cores (all
+    threads), timed on a bounded sample of configs[1] — SAMPLE_VIEWS of the 4 views at the real latent size and CFG —
+    and scaled by the view count (the step is batch-linear: every view runs the same layers on the same shapes)."""
+    from flops import unet_flops
     from helpers import synthetic_inputs
 
     torch.set_num_threads(os.cpu_count() or 1)
-    torch.manual_seed(0)
-    m = MultiViewUNetOracle(None, img_ref_scale=1.0, cam_modulation_strength=1.0).eval()
-    inp = synthetic_inputs(sample_views, latent, 1)
-    args = (inp["latents"], 981, inp["text"], inp["source_camera"], inp["target_camera"], inp["source_latents"])
+    m = model if model is not None else oracle_model()
+    inp = synthetic_inputs(VIEWS, LATENT, CFG)
     times = []
-    with torch.no_grad():
-        for _ in range(1 + reps):  # first call is the warm-up
-            t0 = time.time()
-            m(*args, pos_proj=inp["pos_proj"])
-            times.append(time.time() - t0)
-    sec = min(times[1:])
-    f = unet_flops(latent)
-    sample_flops = sample_views * (f["total"] + f["base"])  # the reference re-runs the frozen UNet every step
-    full_flops = VIEWS * CFG * unet_flops(LATENT)["total"] + VIEWS * unet_flops(LATENT)["base"]
-    steps_per_s = (sample_flops / sec) / full_flops
+    for _ in range(warmup + reps):
+        t0 = time.time()
+        cpu_sample_step(m, inp)
+        times.append(time.time() - t0)
+    timed = times[warmup:]
+    sec = sum(timed) / len(timed)
+    f = unet_flops(LATENT)
+    sample_flops = SAMPLE_VIEWS * (CFG * f["total"] + f["base"])  # the reference re-runs the frozen UNet every step
+    steps_per_s = 1.0 / (sec * VIEWS / SAMPLE_VIEWS)
     return {"value": steps_per_s, "unit": "steps/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"oracle port (fp32 torch CPU) of MultiViewUNet.forward incl. the per-step frozen-UNet re-run, "
-                      f"{sample_views} views x {latent}x{latent} latents = {sample_flops / 1e9:.0f} GFLOP in {sec:.2f} s "
-                      f"(best of {reps} after 1 warm-up), scaled by FLOPs to the {full_flops / 1e12:.2f} TFLOP step the "
-                      f"reference executes", "cpu_tflops": sample_flops / sec / 1e12}
+            "sample": f"oracle port (fp32 torch CPU, full SD2.1 width) of MultiViewUNet.forward incl. the per-step "
+                      f"frozen-UNet re-run: {SAMPLE_VIEWS} of the {VIEWS} views x CFG {CFG} at {LATENT}x{LATENT} latents = "
+                      f"{sample_flops / 1e12:.2f} TFLOP in {sec:.2f} s (mean of {reps} after {warmup} warm-up), x"
+                      f"{VIEWS // SAMPLE_VIEWS} views for the full step", "cpu_tflops": sample_flops / sec / 1e12,
+            "sample_seconds": sec, "sample_fraction": SAMPLE_VIEWS / VIEWS}, timed
+
+
+def parity_check(pipe, sess_latents, dev):
+    """The timed model against the oracle at a size the oracle finishes in seconds (2 views x 32^2, cfg 1), same
+    weights; and sanity of what the timed configuration itself produced."""
+    from helpers import metrics, synthetic_inputs
+
+    unet = pipe.unet
+    saved_shard = unet.shard
+    unet.shard = None
+    o = oracle_model(unet.state_dict())
+    inp = synthetic_inputs(2, 32, 1)
+    cam = unet.camera_encoder
+    saved_proj = cam._pos_proj
+    cam.set_positional_projection(inp["pos_proj"])
+    with torch.no_grad():
+        y_p = unet(inp["latents"].to(dev), 981, inp["text"].to(dev), inp["source_camera"].to(dev),
+                   inp["target_camera"].to(dev), inp["source_latents"].to(dev)).sample
+        y_o = o(inp["latents"], 981, inp["text"], inp["source_camera"], inp["target_camera"], inp["source_latents"],
+                pos_proj=inp["pos_proj"]).sample
+    cam._pos_proj = saved_proj
+    unet.shard = saved_shard
+    m = metrics(y_p, y_o)
+    lat = sess_latents.detach().float().cpu()
+    return {"vs": "fp32 CPU oracle, same weights, 2 views x 32x32 latents, full SD2.1 width", "max_abs": round(m["max_abs"], 5),
+            "normalised_max_abs": round(m["rel"], 5), "cosine": round(m["cos"], 6),
+            "ok": bool(m["rel"] <= 2e-2 and m["cos"] >= 0.999),
+            "timed_config_latents": {"finite": bool(torch.isfinite(lat).all()), "abs_mean": round(float(lat.abs().mean()), 6),
+                                     "checksum": round(float(lat.double().sum()), 4)}}
+
+
+def build_rank_session(dev, sp, pipe, use_graph, guidance=GUIDANCE):
+    """Session of the slice of the object plan `sp` gives this rank (+ the CFG pair exchange when the pair is split)."""
+    from mvd_b200 import dist as mdist
+
+    _, s2, inp, noises = build_session(dev, sp["views_local"], sp["view0"], sp["cfg_local"], sp["cfg_branch"],
+                                       use_graph=use_graph, pipe=pipe, sharded=sp["world"] > 1)
+    if sp["cfg_local"] == 1 and CFG == 2:
+        mdist.install_cfg_pair_exchange(s2, sp, guidance)
+    return s2, inp, noises
 
 
 def run_ours(args):
@@ -216,15 +297,26 @@ def run_ours(args):
     if world not in (1, 2, 4, 8):
         raise SystemExit("supported GPU counts: 1, 2, 4, 8")
     from mvd_b200 import dist as mdist
-    # default multi-GPU mode = sample-parallel (BASELINE.json configs[4]): every GPU denoises its OWN
-    # object (4 views x CFG 2), no data-path collective -> weak scaling; the view-sharded strong-scaling number of
-    # ONE object (configs[2]) is measured afterwards and reported under "view_sharded".
-    plan = mdist.shard_plan(VIEWS, CFG, 1, 0)
-    plan["desc"] = "single GPU" if world == 1 else \
-        f"sample-parallel x{world}: one object (4 views x CFG 2) per GPU, no data-path collective"
-    pipe, sess, inp, noises = build_session(dev, plan["views_local"], plan["view0"], plan["cfg_local"], plan["cfg_branch"],
-                                            use_graph=not args.profile)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        if world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # Headline = ONE object (BASELINE.json configs[1] at N = 1, configs[2] at N > 1): its V x cfg samples are split over
+    # the ranks (strong scaling). Every rank holds the full model; reference features cover all views on every rank.
+    sp = mdist.shard_plan(VIEWS, CFG, world, rank)
+    pipe = build_pipeline(dev)
     if args.profile:  # one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
+        sess, inp, noises = build_rank_session(dev, sp, pipe, use_graph=False)
         for _ in range(2):
             sess.step()
         torch.cuda.synchronize()
@@ -234,14 +326,42 @@ def run_ours(args):
         torch.cuda.profiler.stop()
         print(json.dumps({"profiled_launches": sess.launches_per_step}))
         return
-    sess.capture()
-    torch.cuda.synchronize()
 
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
+    finished = threading.Event()
+    emitted = threading.Lock()
+    result = {}
+
+    def emit(extra=None):
+        if rank != 0 or not emitted.acquire(blocking=False):  # exactly one JSON line
+            return
+        line = dict(result.get("line") or {"metric": METRIC, "value": None, "unit": "steps/s", "n_gpus": world,
+                                            "error": "the timed section did not complete"})
+        line.update(extra or {})
+        print(json.dumps(line))
+        sys.stdout.flush()
+
+    if world > 1:
+        def watchdog():  # a hung collective must never hang the bench: report what we have and leave
+            if not finished.wait(420.0):
+                emit({"watchdog": "timed out after 420 s"})
+                os._exit(0)
+
+        threading.Thread(target=watchdog, daemon=True).start()
+
+    sess, graph_used, err = None, True, None
+    for use_graph in (True, False):  # NCCL inside a captured step (N = 8) falls back to eager launches if capture fails
+        try:
+            sess, inp, noises = build_rank_session(dev, sp, pipe, use_graph)
+            if use_graph:
+                sess.capture()
+            torch.cuda.synchronize()
+            graph_used = use_graph
+            break
+        except Exception as exc:  # noqa: BLE001
+            err = f"{type(exc).__name__}: {exc}"[:300]
+            sess = None
+    if sess is None:
+        raise SystemExit(f"bench.py: could not build the sharded session: {err}")
 
     for _ in range(max(args.warmup, 3)):
         sess.step()
@@ -255,15 +375,13 @@ def run_ours(args):
     e1.record()
     barrier()
     t_wall1 = time.time()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = float(ms.item())
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    timed_latents = sess.latents.clone()
 
     # ---- e2e: host (pinned) latents + noise in, updated latents out, every step, through the session API
-    lat_host = inp["latents"][plan["view0"]:plan["view0"] + plan["views_local"]].contiguous().pin_memory()
+    vs = slice(sp["view0"], sp["view0"] + sp["views_local"])
+    lat_host = inp["latents"][vs].contiguous().pin_memory()
     noise_host = noises[0].contiguous().pin_memory()
     out_host = torch.empty_like(lat_host).pin_memory()
     noise_slot = sess.noise_table[0].view_as(sess.latents)
@@ -283,93 +401,65 @@ def run_ours(args):
     for _ in range(k_e2e):
         e2e_step()
     barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_sps = world * k_e2e / float(e2e_s.item())
+    e2e_sps = k_e2e / max_over_ranks(time.perf_counter() - t0)
 
-    emitted = threading.Lock()
+    pk, how = peaks()
+    steps_per_s = args.steps / (ms_total * 1e-3)  # steps of the ONE object per second
+    result["line"] = {
+        "metric": METRIC, "value": round(steps_per_s, 3), "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD + ", bf16, random-init weights", "views": VIEWS, "cfg": CFG, "latent": LATENT,
+                   "parallelism": sp["desc"], "samples_per_gpu": sp["views_local"] * sp["cfg_local"],
+                   "l2": "working set (1.9 GB weights + activations) >> 126 MB L2; no flush",
+                   "cuda_graph": graph_used, "step_invariant_cached": "reference-UNet features, reference/text K/V, camera emb"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_sps, 3), "unit": "steps/s", "h2d_bytes_per_step": lat_host.numel() * 4 * 2 * world,
+                "d2h_bytes_per_step": out_host.numel() * 4 * world, "steps": k_e2e},
+        "gpu_launches": int(sess.launches_per_step * args.steps * world),
+        "launches_per_step": int(sess.launches_per_step),
+        "step_tflops": round(FLOPS_PER_STEP * steps_per_s / 1e12, 1),
+        "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 / (world * pk["bf16_tflops_sustained"]), 4),
+    }
 
-    def emit(view_sharded):
-        if not emitted.acquire(blocking=False):  # exactly one JSON line
-            return
-        pk, how = peaks()
-        steps_per_s = world * args.steps / (ms_total * 1e-3)  # object-steps per second over all GPUs
-        line = {
-            "metric": "MV denoise steps/s (SD2.1+adapter 512^2, 4 views x CFG 2)", "value": round(steps_per_s, 3),
-            "unit": "steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD + ", bf16, random-init weights", "views": VIEWS, "cfg": CFG, "latent": LATENT,
-                       "parallelism": plan["desc"], "l2": "working set (1.9 GB weights + activations) >> 126 MB L2; no flush",
-                       "cuda_graph": True, "step_invariant_cached": "reference-UNet features, reference/text K/V, camera emb"},
-            "clocks": clocks,
-            "e2e": {"value": round(e2e_sps, 3), "unit": "steps/s", "h2d_bytes_per_step": lat_host.numel() * 4 * 2,
-                    "d2h_bytes_per_step": out_host.numel() * 4, "steps": k_e2e},
-            "gpu_launches": int(sess.launches_per_step * args.steps * world),
-            "launches_per_step": int(sess.launches_per_step),
-            "step_tflops": round(FLOPS_PER_STEP * steps_per_s / 1e12, 1),
-            "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 / (world * pk["bf16_tflops_sustained"]), 4),
-        }
-        if view_sharded is not None:
-            line["view_sharded"] = view_sharded
-        if world == 1:
-            line["roofline"] = attention_roofline(dev, pk, how)
-            if not args.no_cpu_baseline:
-                line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
-        sys.stdout.flush()
+    # ---- N > 1: the zero-communication replica mode (configs[4]) as a side figure
+    if world > 1 and not args.no_replicas:
+        try:
+            pipe.unet.shard = None
+            del sess
+            rp = mdist.shard_plan(VIEWS, CFG, 1, 0)
+            _, s2, _, _ = build_session(dev, rp["views_local"], rp["view0"], rp["cfg_local"], rp["cfg_branch"],
+                                        use_graph=True, pipe=pipe)
+            s2.capture()
+            for _ in range(3):
+                s2.step()
+            barrier()
+            k_sp = max(3, min(args.steps, 10))
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(k_sp):
+                s2.step()
+            v1.record()
+            barrier()
+            sp_ms = max_over_ranks(v0.elapsed_time(v1))
+            result["line"]["sample_parallel"] = {
+                "value": round(world * k_sp / (sp_ms * 1e-3), 3), "unit": "object-steps/s over all GPUs", "scaling": "weak",
+                "ms_per_step": round(sp_ms / k_sp, 3), "steps": k_sp,
+                "parallelism": f"one object (4 views x CFG 2) per GPU x{world}, no data-path collective (configs[4])"}
+        except Exception as exc:  # noqa: BLE001
+            result["line"]["sample_parallel"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
-    # ---- strong scaling of ONE object (configs[2]): views / CFG branches sharded over the ranks
-    view_sharded = None
-    finished = threading.Event()
-    if world > 1:
-        import torch.distributed as dist
-
-        def watchdog():  # the optional section must never hang the bench: after 120 s report what we have and leave
-            if not finished.wait(120.0):
-                if rank == 0:
-                    emit({"error": "timed out after 120 s", "parallelism": "view-sharded"})
-                os._exit(0)
-
-        threading.Thread(target=watchdog, daemon=True).start()
-    run_strong = world > 1 and (world <= VIEWS or args.strong8)
-    if world > 1 and not run_strong:
-        view_sharded = {"skipped": "N = V*cfg needs a per-step NCCL exchange of the CFG pair (mvd_b200/dist.py); "
-                                   "run with --strong8 to time it"}
-    if run_strong:
-        sp = mdist.shard_plan(VIEWS, CFG, world, rank)
-        k_vs = max(3, min(args.steps, 10))
-        for use_graph in (True, False):  # NCCL inside a captured step (N = 8) falls back to eager launches if needed
+    if world == 1 and rank == 0:
+        result["line"]["roofline"] = attention_roofline(dev, pk, how)
+        if not args.no_parity:
             try:
-                _, s2, _, _ = build_session(dev, sp["views_local"], sp["view0"], sp["cfg_local"], sp["cfg_branch"],
-                                            use_graph=use_graph, pipe=pipe)
-                if sp["cfg_local"] == 1 and CFG == 2:
-                    mdist.install_cfg_pair_exchange(s2, sp, GUIDANCE)
-                if use_graph:
-                    s2.capture()
-                for _ in range(3):
-                    s2.step()
-                barrier()
-                v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                v0.record()
-                for _ in range(k_vs):
-                    s2.step()
-                v1.record()
-                barrier()
-                vms = torch.tensor([v0.elapsed_time(v1)], device=dev)
-                dist.all_reduce(vms, op=dist.ReduceOp.MAX)
-                view_sharded = {"value": round(k_vs / (float(vms.item()) * 1e-3), 3), "unit": "steps/s of one object",
-                                "ms_per_step": round(float(vms.item()) / k_vs, 3), "scaling": "strong",
-                                "parallelism": sp["desc"], "cuda_graph": use_graph, "steps": k_vs}
-                break
+                result["line"]["parity"] = parity_check(pipe, timed_latents, dev)
             except Exception as exc:  # noqa: BLE001
-                view_sharded = {"error": f"{type(exc).__name__}: {exc}"[:300], "cuda_graph": use_graph}
-        pipe.unet.shard = None
+                result["line"]["parity"] = {"error": f"{type(exc).__name__}: {exc}"[:300], "ok": False}
+        if not args.no_cpu_baseline:
+            result["line"]["cpu_baseline"] = cpu_baseline()[0]
     finished.set()
-    if rank == 0:
-        emit(view_sharded)
+    emit()
     # All measurements are done and reported. Skip the NCCL teardown on purpose: destroy_process_group() after a
     # CUDA graph that captured NCCL work has been observed to hang on this stack; leaving through os._exit is safe
     # because nothing is left to flush but stdout.
@@ -383,19 +473,25 @@ def run_ours(args):
 # reference arm: the reference's own CPU implementation of the path (oracle port), all host threads
 # ------------------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """K timed steps (after W warm-ups), each step = the bounded sample cpu_sample_step() of the configs[1] step (1 of
+    the 4 views, both CFG branches, 64^2 latents, full-width model, incl. the per-step frozen-UNet re-run). `value` is
+    the full-configuration figure (x4 views); `ms_per_step` is the measured time of one timed (sample) step, so that
+    steps x ms_per_step is the wall time of the timed region."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    k, w = max(1, min(args.steps, 3)), 1
-    best = cpu_baseline(reps=k)
+    k, w = max(1, args.steps), max(0, args.warmup)
+    best, timed = cpu_baseline(reps=k, warmup=w)
     v = best["value"]
     line = {
-        "impl": "reference", "metric": "MV denoise steps/s (SD2.1+adapter 512^2, 4 views x CFG 2)", "value": v,
-        "unit": "steps/s", "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": k, "warmup": w,
-        "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD + ", fp32 on the host cores, random-init weights; timed on a bounded sample "
-                               "(cpu_baseline.sample) and scaled by FLOPs", "views": VIEWS, "cfg": CFG, "latent": LATENT},
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "steps/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": k, "warmup": w,
+        "ms_per_step": 1e3 * sum(timed) / len(timed), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD + ", fp32 on the host cores, random-init weights; every timed step is a bounded "
+                               f"sample ({SAMPLE_VIEWS} of {VIEWS} views, see cpu_baseline.sample) and `value` is scaled to "
+                               "the full step", "views": VIEWS, "cfg": CFG, "latent": LATENT,
+                   "sample_fraction": SAMPLE_VIEWS / VIEWS},
         "cpu_baseline": best,
         "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -410,7 +506,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--strong8", action="store_true", help="also time the view x CFG sharded mode at 8 GPUs")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed model (N = 1)")
+    ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the sample-parallel (replica) side figure")
     ap.add_argument("--profile", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
     if args.impl == "reference":

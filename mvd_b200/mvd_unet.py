@@ -154,8 +154,28 @@ class MultiViewUNet(nn.Module):
             elif text.shape[0] > batch_size:
                 ie_text = text[:batch_size]
             shard = self.shard
-            sharded = shard is not None and shard["views_local"] * shard.get("cfg_total", 2) != 0 and \
-                batch_size == shard["views_total"] and shard["views_local"] < shard["views_total"]
+            sharded = False
+            if shard is not None:
+                # A rank owns views_local x cfg_local of the views_total x cfg_total samples of the object; it is
+                # sharded as soon as EITHER dimension is split (one view with its CFG pair on two ranks included:
+                # the unconditional rank must still feed the conditional text to the image encoder,
+                # mvd_unet.py:280-283).
+                cfg_total = int(shard.get("cfg_total", 2))
+                if sample.shape[0] % shard["views_local"]:
+                    raise ValueError(f"sharded step: local batch {sample.shape[0]} is not a multiple of views_local "
+                                     f"{shard['views_local']}")
+                cfg_local = sample.shape[0] // shard["views_local"]
+                if cfg_local not in (1, cfg_total):
+                    raise ValueError(f"sharded step: local batch holds {cfg_local} CFG branches of {cfg_total}")
+                if batch_size != shard["views_total"]:
+                    raise ValueError("sharded step: source_image_latents must hold ALL views of the object "
+                                     f"({shard['views_total']}), got {batch_size}: the reference normalisation "
+                                     "(attention.py:95-103) couples the batch")
+                if cfg_total > 1 and not self.matched_batch_cfg:
+                    raise ValueError("view/CFG sharding needs matched_batch_cfg=True: the reference-literal flat "
+                                     "re-view of un-repeated features (attention.py:130-132) mixes the samples of "
+                                     "different ranks")
+                sharded = shard["views_local"] * cfg_local < shard["views_total"] * cfg_total
             if sharded:  # features for ALL views (batch-coupled normalisation), conditional text of all views
                 ie_text = self._prepare_text(shard["ie_text"].to(device=dev), batch_size)
             features = self.image_encoder(latents=source_image_latents.to(device=dev), text_embeddings=ie_text,

@@ -30,6 +30,19 @@ def test_shard_plan_partitions_all_samples(world):
     assert sorted(seen) == list(range(views * cfg))
 
 
+@pytest.mark.parametrize("views,cfg,world", [(4, 2, 1), (4, 2, 2), (4, 2, 4), (4, 2, 8), (1, 2, 2), (8, 1, 8), (8, 2, 16)])
+def test_local_sample_index_stays_inside_the_reference_batch(views, cfg, world):
+    """Indices address the [cfg_total * V] matched-batch reference features; every rank's index set is in range and
+    the union covers each sample exactly once (the out-of-range gather ADVICE.md flagged cannot be built)."""
+    seen = []
+    for rank in range(world):
+        p = shard_plan(views, cfg, world, rank)
+        idx = local_sample_index(views, cfg, p["view0"], p["views_local"], p["cfg_local"], p["cfg_branch"])
+        assert all(0 <= i < views * cfg for i in idx)
+        seen += idx
+    assert sorted(seen) == list(range(views * cfg))
+
+
 def test_shard_plan_rejects_bad_world_sizes():
     with pytest.raises(ValueError):
         shard_plan(4, 2, 3, 0)

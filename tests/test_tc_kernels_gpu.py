@@ -126,13 +126,19 @@ def test_conv3x3_stride2(n, h, w, c):
          atol=3e-2)
 
 
-def test_conv3x3_two_source():
+@pytest.mark.parametrize("n,hw,c1,c2,cout", [(2, 32, 640, 320, 640), (2, 16, 1280, 1280, 1280), (2, 8, 1280, 1280, 1280),
+                                              (1, 16, 1280, 640, 1280)])
+def test_conv3x3_two_source(n, hw, c1, c2, cout):
+    """Channel-concatenated skip connections of the up path (two tensor maps, one k-loop), incl. the 1280+1280 sites
+    of up_blocks[0..1] at the 16x16 / 8x8 levels and the 1280+640 one."""
     from mvd_b200 import ops
 
-    x = _randn(2, 32, 32, 640, seed=1)
-    x2 = _randn(2, 32, 32, 320, seed=5)
-    w9 = _randn(640, 9 * 960, scale=(9 * 960) ** -0.5, seed=2)
-    _cmp(ops.conv3x3(x, w9, x2=x2), _conv_ref(x, w9, None, None, None, 1, x2=x2), "conv two-source", atol=3e-2)
+    x = _randn(n, hw, hw, c1, seed=1)
+    x2 = _randn(n, hw, hw, c2, seed=5)
+    w9 = _randn(cout, 9 * (c1 + c2), scale=(9 * (c1 + c2)) ** -0.5, seed=2)
+    b = _randn(cout, seed=3)
+    _cmp(ops.conv3x3(x, w9, bias=b, x2=x2), _conv_ref(x, w9, b, None, None, 1, x2=x2),
+         f"conv two-source {c1}+{c2}->{cout} @{hw}", atol=3e-2)
 
 
 def _attn_ref(q, k, v, heads, scale):
