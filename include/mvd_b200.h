@@ -49,7 +49,9 @@ int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t 
                     int geglu, int tile_n, void* stream);
 
 /* 3x3 convolution, padding 1, stride 1 or 2, NHWC bf16, implicit GEMM.
- * out[n, y, x, :] = sum_taps [x | x2](n, s*y+ky-1, s*x+kx-1, :) @ w[:, ky, kx, :]^T + bias + img_bias[n, :] (fp32, row stride img_bias_ld)
+ * out[n, y, x, :] = sum_taps [x | x2](n, s*y+ky-1, s*x+kx-1, :) @ w[:, ky, kx, :]^T + bias + img_bias[n, :] (fp32, row stride
+ *                   img_bias_ld floats, a multiple of 4; 0 = ONE row shared by every image, e.g. the time-embedding
+ *                   projection of a scalar timestep)
  *                   (+ residual[n, y, x, :]).
  * Replaces diffusers ResnetBlock2D.conv1/conv2, Downsample2D.conv (stride 2), Upsample2D.conv
  * (invoked from src/models/mvd_unet.py:318 and src/models/image_encoder.py:105).
@@ -58,6 +60,37 @@ int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t 
 int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
                      const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
                      int w_out, int c_out, int stride, int tile_n, void* stream);
+
+/* Optional fused neighbours of a GEMM / conv launch (mvd_linear_ex_bf16, mvd_conv3x3_ex_bf16); every pointer may be NULL.
+ *  - LayerNorm of the A rows folded into the GEMM (diffusers BasicTransformerBlock.norm1/2/3 in front of attn1 / attn2 /
+ *    ff): the caller passes weights already scaled by gamma per input channel, `ln_colsum[n]` =
+ *    sum_k of the scaled bf16 weight row n (fp32), folds W.beta into the bias, and `ln_stats` = [M][ln_parts][2] fp32
+ *    partial (sum x, sum x^2) of each A row as written by the producing launch's `stats_out`. The epilogue computes
+ *    rstd * (acc - mean * ln_colsum[n]) — identical to LayerNorm followed by the GEMM, one kernel and one pass less.
+ *  - stats_out: [M][stats_parts][2] fp32 partial row statistics of the bf16 OUTPUT, one pair per column tile
+ *    (stats_parts must equal the launch's column-tile count: mvd_gemm_plan's ceil(N / bn)); plain linears only.
+ *  - FiLM on the output (src/models/camera_encoder.py:221-234 applied by the forward hooks of src/models/mvd_unet.py:
+ *    354-385 to a block's output): out = v * film_scale[g][n] + film_shift[g][n], g = image (conv) or row group
+ *    (linear, rows_per_group), fp32 rows of stride film_ld. */
+typedef struct mvd_gemm_extras {
+  const float* ln_stats;
+  const float* ln_colsum;
+  int ln_parts;
+  float ln_eps;
+  float* stats_out;
+  int stats_parts;
+  const float* film_scale;
+  const float* film_shift;
+  int film_ld;
+} mvd_gemm_extras;
+
+int mvd_linear_ex_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
+                       int64_t ldw, const void* bias, const float* row_group_bias, int row_group_bias_ld,
+                       int rows_per_group, const void* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
+                       int geglu, int tile_n, const mvd_gemm_extras* extras, void* stream);
+int mvd_conv3x3_ex_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
+                        const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
+                        int w_out, int c_out, int stride, int tile_n, const mvd_gemm_extras* extras, void* stream);
 
 /* The scheduling decision mvd_linear_bf16 (n_img = h_out = 1, w_out = M, ntaps = 1) / mvd_conv3x3_bf16 (ntaps = 9)
  * would take for a problem, without launching anything: tile width, whether the weight tile stays resident in shared
@@ -84,6 +117,8 @@ int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_stride, const
  * zero-filled once, private to launches that cannot run concurrently, e.g. one per stream). With it, the units of a
  * launch's last partial wave are split along S_kv over the idle SMs and merged by whichever CTA finishes a unit last
  * (deterministic part order); without it (NULL) every (256-row tile pair, head, batch) unit runs on one CTA.
+ * co_units: number of such units of OTHER attention launches the caller has in flight on another stream (0 if none):
+ * the last wave is then shared with them and only this launch's share of it is split.
  * k_batch_stride = v_batch_stride = 0 shares one K/V sequence between all batch entries: the cross-view reference
  * mode of configs[3], where every view attends over the concatenated tokens of all views
  * (src/models/attention.py:190-197 accepts a 3-D reference; :126-132 projects it once). */
@@ -91,7 +126,7 @@ int64_t mvd_attention_workspace_bytes(void);
 int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch_stride, const void* k, int64_t ldk,
                           int64_t k_batch_stride, const void* v, int64_t ldv, int64_t v_batch_stride, void* out,
                           int64_t ldo, int64_t o_batch_stride, int batch, int heads, int s_q, int s_kv, float scale,
-                          void* workspace, int64_t workspace_bytes, void* stream);
+                          void* workspace, int64_t workspace_bytes, int co_units, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Bandwidth-bound normalisation kernels, csrc/norm.cu
@@ -182,6 +217,12 @@ int mvd_cfg_ddpm_step_f32(const float* model_out, float* latents, const float* n
 int mvd_cfg_ddpm_step_table_f32(const float* model_out, float* latents, const float* noise_table, int64_t n, int cfg,
                                 float guidance, const float* coef_table, const int* step_idx, void* stream);
 int mvd_advance_step(int* step_idx, const float* coef_table, float* timestep_out, int n_steps, void* stream);
+/* mvd_advance_step that additionally copies row *step_idx (after the increment) of row_table [n_steps][row_len] fp32
+ * into row_out: the per-schedule table of everything that depends on the timestep only — diffusers Timesteps +
+ * TimestepEmbedding + the 22 ResnetBlock2D.time_emb_proj(SiLU(temb)) outputs, computed once
+ * per session instead of once per step. row_len multiple of 4, rows 16-byte aligned. */
+int mvd_advance_step_rows(int* step_idx, const float* coef_table, float* timestep_out, int n_steps,
+                          const float* row_table, float* row_out, int row_len, void* stream);
 
 #ifdef __cplusplus
 }

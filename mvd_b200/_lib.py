@@ -51,10 +51,12 @@ _SIGNATURES = {
     "mvd_kernel_launch_count": (_L, []),
     "mvd_linear_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "mvd_conv3x3_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
+    "mvd_linear_ex_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
+    "mvd_conv3x3_ex_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mvd_gemm_plan": (_I, [_I] * 9 + [_P] * 3),
     "mvd_attention_bf16": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P]),
     "mvd_attention_workspace_bytes": (_L, []),
-    "mvd_attention_bf16_ws": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P, _L, _P]),
+    "mvd_attention_bf16_ws": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P, _L, _I, _P]),
     "mvd_groupnorm_workspace_floats": (_L, [_I, _I, _I]),
     "mvd_groupnorm_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _I, _I, _F, _I, _P, _L, _P]),
     "mvd_layernorm_bf16": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _F, _P]),
@@ -74,6 +76,7 @@ _SIGNATURES = {
     "mvd_cfg_ddpm_step_f32": (_I, [_P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _F, _P]),
     "mvd_cfg_ddpm_step_table_f32": (_I, [_P, _P, _P, _L, _I, _F, _P, _P, _P]),
     "mvd_advance_step": (_I, [_P, _P, _P, _I, _P]),
+    "mvd_advance_step_rows": (_I, [_P, _P, _P, _I, _P, _P, _I, _P]),
 }
 
 

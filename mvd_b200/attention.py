@@ -23,7 +23,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .unet import BF16, AttnProcessor2_0, _bf16, _versions, nhwc_view
+from .unet import BF16, AttnProcessor2_0, LNInput, _bf16, _versions, fold_layernorm, nhwc_view
 
 
 def log_debug(file_path, message):  # reference src/utils.py:25-34; callers here never build tensor f-strings
@@ -94,6 +94,16 @@ class ImageCrossAttentionProcessor(nn.Module):
         self.__dict__["_ref_cache"] = None
         return p
 
+    def _ln_pack(self, attn, norm: nn.LayerNorm, pk):
+        """[q | k | v | q_ref] (or [q | q_ref]) with the block's LayerNorm folded in (unet.fold_layernorm)."""
+        key = (id(pk), _versions(norm.weight, norm.bias))
+        hit = self.__dict__.get("_ln_cache")
+        if hit is None or hit[0] != key or hit[2] is not pk:
+            with torch.no_grad():
+                hit = (key, fold_layernorm(pk["w_in"], norm), pk)
+            self.__dict__["_ln_cache"] = hit
+        return hit[1]
+
     # ---- step-invariant reference K/V ---------------------------------------------------------------------
     def _reference_kv(self, ref: torch.Tensor, pk) -> torch.Tensor:
         """[B_ref * S_kv, 2C] = [to_k_ref(r) | to_v_ref(r)], r = normalised reference (attention.py:95-132)."""
@@ -139,17 +149,25 @@ class ImageCrossAttentionProcessor(nn.Module):
                  attention_mask: Optional[torch.Tensor] = None, temb: Optional[torch.Tensor] = None,
                  ref_hidden_states: Optional[Dict[str, torch.Tensor]] = None,
                  residual: Optional[torch.Tensor] = None, ref_batch_index: Optional[torch.Tensor] = None,
-                 *args, **kwargs) -> torch.Tensor:
+                 ln_fold: Optional[LNInput] = None, want_stats: bool = False, *args, **kwargs):
+        """Extensions of the diffusers protocol used by mvd_b200's own transformer block (a stock caller never
+        passes them): `residual` (added in the output projection's epilogue), `ln_fold` (hidden_states is the RAW
+        residual stream and the block's LayerNorm is folded into the input projection), `want_stats` (return
+        (out, ops.RowStats) so the next LayerNorm can be folded too)."""
         kwargs.pop("debug_log_file_path", None)
         native = isinstance(self.original_processor, AttnProcessor2_0)
         if ref_hidden_states is None or self.name not in ref_hidden_states:
             # reference attention.py:72-81: silently fall through to the original processor
             if native:
                 return self.original_processor(attn, hidden_states, encoder_hidden_states, attention_mask, temb=temb,
-                                               residual=residual)
+                                               residual=residual, ln_fold=ln_fold, want_stats=want_stats)
+            if ln_fold is not None:
+                hidden_states = ops.layernorm(hidden_states, _bf16(ln_fold.norm.weight), _bf16(ln_fold.norm.bias),
+                                              ln_fold.norm.eps)
             out = self.original_processor(attn, hidden_states, encoder_hidden_states, attention_mask, temb=temb,
                                           *args, **kwargs)
-            return out if residual is None else ops.add(out.contiguous(), residual.contiguous())
+            out = out if residual is None else ops.add(out.contiguous(), residual.contiguous())
+            return (out, None) if want_stats else out
         if attention_mask is not None:
             raise NotImplementedError("attention masks are not on MVD's hot path")
         if hidden_states.dim() != 3:
@@ -177,13 +195,19 @@ class ImageCrossAttentionProcessor(nn.Module):
 
         if pk["fused"]:
             cat = torch.empty((b, s, 2 * c), device=hidden_states.device, dtype=BF16)
+            if ln_fold is not None:
+                wg, colsum, cst = self._ln_pack(attn, ln_fold.norm, pk)
+                proj = ops.linear(hs2d, wg, row_group_bias=cst, rows_per_group=b * s,
+                                  ln=ops.LNFold(ln_fold.stats, colsum, ln_fold.norm.eps))
+            else:
+                proj = ops.linear(hs2d, pk["w_in"])
             if pk["is_cross"]:
-                proj = ops.linear(hs2d, pk["w_in"]).view(b, s, 2 * c)
+                proj = proj.view(b, s, 2 * c)
                 q, q_ref = proj[:, :, :c], proj[:, :, c:]
                 kv = attn.context_kv(encoder_hidden_states)
                 k, v = kv[:, :, :c], kv[:, :, c:]
             else:
-                proj = ops.linear(hs2d, pk["w_in"]).view(b, s, 4 * c)
+                proj = proj.view(b, s, 4 * c)
                 q, k, v, q_ref = (proj[:, :, i * c:(i + 1) * c] for i in range(4))
             # The two branches are independent until the fused out-projection. Each launch is a non-integral
             # number of one-CTA-per-SM waves, so the reference branch is forked onto a second stream to fill the
@@ -193,19 +217,29 @@ class ImageCrossAttentionProcessor(nn.Module):
                 side = _branch_stream(hidden_states.device)
                 fork, join = torch.cuda.Event(), torch.cuda.Event()
                 fork.record(main)
+                # the side launch goes first and finishes first: it never owns the machine's last wave, so only the
+                # main launch splits a tail, and only its share of the COMBINED last wave (co_units)
                 with torch.cuda.stream(side):
                     side.wait_event(fork)
-                    ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:])
+                    ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:], split_tail=False)
                     join.record(side)
-                ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])
+                ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c],
+                              co_units=ops.attention_units(b, self.heads, s))
                 main.wait_event(join)
             else:
                 ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])
                 ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:])
-            out = ops.linear(cat.view(b * s, 2 * c), pk["w_out"], bias=pk["b_out"], residual=res2d)
+            out = ops.linear(cat.view(b * s, 2 * c), pk["w_out"], bias=pk["b_out"], residual=res2d,
+                             want_stats=want_stats)
+            if want_stats:
+                return out[0].view(b, s, c), out[1]
             return out.view(b, s, c)
 
         # foreign original processor (e.g. a stock diffusers processor): run it as is, add our branch on top
+        if ln_fold is not None:
+            hidden_states = ops.layernorm(hidden_states, _bf16(ln_fold.norm.weight), _bf16(ln_fold.norm.bias),
+                                          ln_fold.norm.eps)
+            hs2d = hidden_states.reshape(b * s, c)
         original = self.original_processor(attn, hidden_states, encoder_hidden_states, attention_mask, temb=temb,
                                            *args, **kwargs)
         base = original.reshape(b * s, c).contiguous()
@@ -213,7 +247,10 @@ class ImageCrossAttentionProcessor(nn.Module):
             base = ops.add(base, res2d.contiguous())
         q_ref = ops.linear(hs2d, pk["wq_ref"]).view(b, s, c)
         o = ops.attention(q_ref, k_ref, v_ref, self.heads, scale)
-        return ops.linear(o.view(b * s, c), pk["w_out"], bias=pk["b_out"], residual=base).view(b, s, c)
+        out = ops.linear(o.view(b * s, c), pk["w_out"], bias=pk["b_out"], residual=base, want_stats=want_stats)
+        if want_stats:
+            return out[0].view(b, s, c), out[1]
+        return out.view(b, s, c)
 
     def _adapt_reference_features(self, reference_states, target_dim):
         """reference attention.py:190-197 (kept for API parity): NCHW -> [B, HW, C] view."""

@@ -154,6 +154,28 @@ class CameraEncoder(nn.Module):
             cache[modulator_name] = mod
         return mod
 
+    def film_coefficients(self, modulator_name: str, camera_embedding: torch.Tensor, batch: int):
+        """(scale, shift) fp32 [batch, C] of apply_modulation_to_tensor: scale = 2*sigmoid(s)*strength,
+        shift = shift*strength (camera_encoder.py:221-234), sample n using camera n % V — for producers that apply the
+        FiLM in their own epilogue. Cached with the modulator output (constant across denoise steps)."""
+        if modulator_name not in self.modulators or camera_embedding is None:
+            return None
+        mod = self.modulation(modulator_name, camera_embedding)
+        key = (modulator_name, mod.data_ptr(), mod._version, batch, float(self.modulation_strength))
+        cache = self.__dict__.setdefault("_film_cache", {})
+        hit = cache.get(modulator_name)
+        if hit is None or hit[0] != key:
+            v, c2 = mod.shape
+            c = c2 // 2
+            if batch % v:
+                raise ValueError(f"batch {batch} is not a multiple of the camera count {v}")
+            strength = float(self.modulation_strength)
+            scale = (2.0 * strength * torch.sigmoid(mod[:, :c])).repeat(batch // v, 1).contiguous()
+            shift = (strength * mod[:, c:]).repeat(batch // v, 1).contiguous()
+            hit = (key, (scale, shift), mod)
+            cache[modulator_name] = hit
+        return hit[1]
+
     def apply_modulation(self, hidden_states, modulator_name: str, camera_embedding: torch.Tensor):
         if isinstance(hidden_states, tuple):  # down blocks: only the main output is modulated (:201-205)
             return (self.apply_modulation_to_tensor(hidden_states[0], modulator_name, camera_embedding),) + \

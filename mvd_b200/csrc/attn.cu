@@ -732,7 +732,8 @@ extern "C" int64_t mvd_attention_workspace_bytes(void) { return kWsOBytes + kWsM
 extern "C" int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch_stride, const void* k, int64_t ldk,
                                      int64_t k_batch_stride, const void* v, int64_t ldv, int64_t v_batch_stride,
                                      void* out, int64_t ldo, int64_t o_batch_stride, int batch, int heads, int s_q,
-                                     int s_kv, float scale, void* workspace, int64_t workspace_bytes, void* stream) {
+                                     int s_kv, float scale, void* workspace, int64_t workspace_bytes, int co_units,
+                                     void* stream) {
   using namespace mvd;
   MVD_CHECK(batch > 0 && heads > 0 && s_q > 0 && s_kv > 0, "attention: empty problem B=%d H=%d Sq=%d Skv=%d", batch,
             heads, s_q, s_kv);
@@ -792,7 +793,11 @@ extern "C" int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch
     sc.n_full = static_cast<int>(units);
     sc.split = 1;
     const int n_blocks = (s_kv + ATT_BN - 1) / ATT_BN;
-    const int rem = static_cast<int>(units % sms);
+    // co_units: 256-row units of OTHER launches the caller runs concurrently (the adapter's second attention branch on
+    // a side stream): the machine's last wave is then shared, and only what this launch contributes to it is split
+    MVD_CHECK(co_units >= 0, "attention: co_units must be >= 0");
+    const int rem = static_cast<int>((units + co_units) % sms) <= units ? static_cast<int>((units + co_units) % sms)
+                                                                         : static_cast<int>(units);
     static const bool split_on = [] {
       const char* e = getenv("MVD_ATTN_SPLIT");
       return e == nullptr || e[0] != '0';
@@ -842,5 +847,5 @@ extern "C" int mvd_attention_bf16(const void* q, int64_t ldq, int64_t q_batch_st
                                   void* out, int64_t ldo, int64_t o_batch_stride, int batch, int heads, int s_q,
                                   int s_kv, float scale, void* stream) {
   return mvd_attention_bf16_ws(q, ldq, q_batch_stride, k, ldk, k_batch_stride, v, ldv, v_batch_stride, out, ldo,
-                               o_batch_stride, batch, heads, s_q, s_kv, scale, nullptr, 0, stream);
+                               o_batch_stride, batch, heads, s_q, s_kv, scale, nullptr, 0, 0, stream);
 }

@@ -444,6 +444,26 @@ __global__ void advance_step_kernel(int* step_idx, const float* coef_table, floa
   timestep_out[0] = coef_table[static_cast<int64_t>(s) * 8];
 }
 
+// Same, plus: copies row `s` (the NEW step) of row_table [n_steps][row_len] into row_out — the per-schedule table of
+// everything that depends on the timestep only (time-embedding MLP + the 22 time_emb_proj outputs), so that the
+// per-step graph carries no timestep arithmetic at all. One block; every thread reads the old counter before thread
+// 0 overwrites it.
+__global__ void __launch_bounds__(1024) advance_step_rows_kernel(int* step_idx, const float* coef_table,
+                                                                 float* timestep_out, int n_steps,
+                                                                 const float4* row_table, float4* row_out, int row_len4) {
+  pdl_wait();
+  pdl_launch_dependents();
+  int s = *step_idx + 1;
+  if (s >= n_steps) s = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    *step_idx = s;
+    timestep_out[0] = coef_table[static_cast<int64_t>(s) * 8];
+  }
+  const float4* src = row_table + static_cast<int64_t>(s) * row_len4;
+  for (int i = threadIdx.x; i < row_len4; i += blockDim.x) row_out[i] = src[i];
+}
+
 }  // namespace mvd
 
 extern "C" {
@@ -651,6 +671,22 @@ int mvd_advance_step(int* step_idx, const float* coef_table, float* timestep_out
             "advance_step: bad arguments");
   MVD_CUDA(launch_pdl(advance_step_kernel, dim3(1), dim3(1), 0, static_cast<cudaStream_t>(stream), step_idx, coef_table,
                       timestep_out, n_steps));
+  MVD_CUDA(cudaGetLastError());
+  count_launches(1);
+  return MVD_OK;
+}
+
+int mvd_advance_step_rows(int* step_idx, const float* coef_table, float* timestep_out, int n_steps,
+                          const float* row_table, float* row_out, int row_len, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(step_idx != nullptr && coef_table != nullptr && timestep_out != nullptr && n_steps > 0 &&
+                row_table != nullptr && row_out != nullptr && row_len > 0 && row_len % 4 == 0,
+            "advance_step_rows: bad arguments");
+  MVD_CHECK(((reinterpret_cast<uintptr_t>(row_table) | reinterpret_cast<uintptr_t>(row_out)) & 15) == 0,
+            "advance_step_rows: rows must be 16-byte aligned");
+  MVD_CUDA(launch_pdl(advance_step_rows_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), step_idx,
+                      coef_table, timestep_out, n_steps, reinterpret_cast<const float4*>(row_table),
+                      reinterpret_cast<float4*>(row_out), row_len / 4));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;

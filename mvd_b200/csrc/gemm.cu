@@ -50,6 +50,21 @@ struct GemmArgs {
   int img_max;           // clamp for the img index (padded rows of the last tile)
   const __nv_bfloat16* bias;  // [N] (permuted like the weight rows when geglu)
   const float* img_bias;      // [imgs, img_bias_ld] fp32 (e.g. time-embedding projection)
+  // --- fused neighbours of the GEMM (all optional)
+  // LayerNorm of the A rows folded into the GEMM: the weights carry gamma, and per output row
+  //   v = rstd * (acc - mean * ln_colsum[col]);  mean / rstd from ln_parts partial (sum, sum of squares) pairs
+  const float2* ln_stats;     // [rows][ln_parts]
+  const float* ln_colsum;     // [N] fp32: sum_k of the (gamma-scaled, bf16) weight row
+  int ln_parts;
+  float ln_inv_k, ln_eps;
+  // row statistics of the bf16 OUTPUT for the LayerNorm that follows: partial (sum, sum of squares) per row and
+  // column tile, [rows][tiles_n]
+  float2* stats_out;
+  int rows_total;             // M (linear mode)
+  // FiLM on the output (camera modulation of a block output): v = v * film_scale[img][col] + film_shift[img][col]
+  const float* film_scale;
+  const float* film_shift;
+  int film_ld;
 };
 
 constexpr int WS_MAX_KBLOCKS = 5;  // weight-stationary tiles: K <= 320
@@ -293,6 +308,21 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const uint32_t t_acc = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
       int img = ln + n0 + (x0 + lx) / p.rows_per_img;
       img = img < p.img_max ? img : p.img_max;
+      float ln_mean = 0.f, ln_rstd = 1.f;
+      if (p.ln_stats != nullptr) {  // linear mode: this lane's row is x0 + lx
+        const int grow = (x0 + lx) < p.rows_total ? (x0 + lx) : p.rows_total - 1;
+        const float2* st = p.ln_stats + static_cast<size_t>(grow) * p.ln_parts;
+        float s1 = 0.f, s2 = 0.f;
+        for (int pp = 0; pp < p.ln_parts; ++pp) {  // fixed order: deterministic
+          const float2 t2 = __ldg(st + pp);
+          s1 += t2.x;
+          s2 += t2.y;
+        }
+        ln_mean = s1 * p.ln_inv_k;
+        ln_rstd = rsqrtf(fmaxf(fmaf(s2, p.ln_inv_k, -ln_mean * ln_mean), 0.f) + p.ln_eps);
+      }
+      const float ln_k2 = -ln_rstd * ln_mean;  // v = rstd * acc + (k2 * colsum + c): two FFMAs per element
+      float st_sum = 0.f, st_sq = 0.f;
 
       for (int c = 0; c < n_chunks; ++c, ++g) {
         const uint32_t buf = g % EPI_BUFS;
@@ -326,6 +356,19 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
           }
           if (col0 + 32 <= p.N) {  // N is a multiple of 32: a chunk is either fully inside or fully outside
+            if (p.ln_stats != nullptr) {
+              // LayerNorm fold fused with the fp32 constant (W.beta + bias, passed as the row-group bias row)
+              const float4* cs = reinterpret_cast<const float4*>(p.ln_colsum + col0);
+              const float4* cb = reinterpret_cast<const float4*>(p.img_bias + static_cast<size_t>(img) * p.img_bias_ld + col0);
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const float4 f = __ldg(cs + q4), c4 = __ldg(cb + q4);
+                v[q4 * 4 + 0] = fmaf(v[q4 * 4 + 0], ln_rstd, fmaf(f.x, ln_k2, c4.x));
+                v[q4 * 4 + 1] = fmaf(v[q4 * 4 + 1], ln_rstd, fmaf(f.y, ln_k2, c4.y));
+                v[q4 * 4 + 2] = fmaf(v[q4 * 4 + 2], ln_rstd, fmaf(f.z, ln_k2, c4.z));
+                v[q4 * 4 + 3] = fmaf(v[q4 * 4 + 3], ln_rstd, fmaf(f.w, ln_k2, c4.w));
+              }
+            } else {
             if (p.bias != nullptr) {
               const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);  // 64-byte aligned
 #pragma unroll
@@ -345,6 +388,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                 const float4 f = __ldg(ib + q4);
                 v[q4 * 4 + 0] += f.x; v[q4 * 4 + 1] += f.y; v[q4 * 4 + 2] += f.z; v[q4 * 4 + 3] += f.w;
               }
+            }
             }
           }
         } else {
@@ -373,10 +417,22 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               bg[q4 * 8 + 4] = g2.x; bg[q4 * 8 + 5] = g2.y; bg[q4 * 8 + 6] = g3.x; bg[q4 * 8 + 7] = g3.y;
             }
           }
+          if (p.ln_stats != nullptr) {  // LayerNorm folded into both halves (column sums follow the weight rows)
+            const float4* ca = reinterpret_cast<const float4*>(p.ln_colsum + wa);
+            const float4* cg = reinterpret_cast<const float4*>(p.ln_colsum + wg);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float a = __uint_as_float(ra[j]) + ba[j];
-            const float gt = __uint_as_float(rg[j]) + bg[j];
+            for (int q4 = 0; q4 < 8; ++q4) {
+              const float4 fa = __ldg(ca + q4), fg = __ldg(cg + q4);
+              ba[q4 * 4 + 0] = fmaf(fa.x, ln_k2, ba[q4 * 4 + 0]); bg[q4 * 4 + 0] = fmaf(fg.x, ln_k2, bg[q4 * 4 + 0]);
+              ba[q4 * 4 + 1] = fmaf(fa.y, ln_k2, ba[q4 * 4 + 1]); bg[q4 * 4 + 1] = fmaf(fg.y, ln_k2, bg[q4 * 4 + 1]);
+              ba[q4 * 4 + 2] = fmaf(fa.z, ln_k2, ba[q4 * 4 + 2]); bg[q4 * 4 + 2] = fmaf(fg.z, ln_k2, bg[q4 * 4 + 2]);
+              ba[q4 * 4 + 3] = fmaf(fa.w, ln_k2, ba[q4 * 4 + 3]); bg[q4 * 4 + 3] = fmaf(fg.w, ln_k2, bg[q4 * 4 + 3]);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {  // ln_rstd == 1 without the fold
+            const float a = fmaf(__uint_as_float(ra[j]), ln_rstd, ba[j]);
+            const float gt = fmaf(__uint_as_float(rg[j]), ln_rstd, bg[j]);
             v[j] = a * gelu_erf(gt);
           }
         }
@@ -390,6 +446,27 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                          f3 = unpack_bf16x2(rv.w);
             v[ch * 8 + 0] += f0.x; v[ch * 8 + 1] += f0.y; v[ch * 8 + 2] += f1.x; v[ch * 8 + 3] += f1.y;
             v[ch * 8 + 4] += f2.x; v[ch * 8 + 5] += f2.y; v[ch * 8 + 6] += f3.x; v[ch * 8 + 7] += f3.y;
+          }
+        }
+        if (p.film_scale != nullptr && col0 + 32 <= n_out) {
+          const float4* fs = reinterpret_cast<const float4*>(p.film_scale + static_cast<size_t>(img) * p.film_ld + col0);
+          const float4* fb = reinterpret_cast<const float4*>(p.film_shift + static_cast<size_t>(img) * p.film_ld + col0);
+#pragma unroll
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 a4 = __ldg(fs + q4), b4 = __ldg(fb + q4);
+            v[q4 * 4 + 0] = fmaf(v[q4 * 4 + 0], a4.x, b4.x);
+            v[q4 * 4 + 1] = fmaf(v[q4 * 4 + 1], a4.y, b4.y);
+            v[q4 * 4 + 2] = fmaf(v[q4 * 4 + 2], a4.z, b4.z);
+            v[q4 * 4 + 3] = fmaf(v[q4 * 4 + 3], a4.w, b4.w);
+          }
+        }
+        if (p.stats_out != nullptr && col0 < n_out) {
+          // statistics of the fp32 values (the stored ones are their bf16 roundings: zero-mean noise of 2^-9 relative
+          // size per element, which changes mean and variance of a >= 320-wide row by less than 1e-4 relative)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            st_sum += v[j];
+            st_sq = fmaf(v[j], v[j], st_sq);
           }
         }
 #pragma unroll
@@ -408,6 +485,8 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_store_commit();
         }
       }
+      if (p.stats_out != nullptr && ln == 0 && x0 + lx < p.rows_total)
+        p.stats_out[static_cast<size_t>(x0 + lx) * p.tiles_n + n_tile] = make_float2(st_sum, st_sq);
       // accumulator fully read -> hand the TMEM stage back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -554,7 +633,8 @@ struct OperandA {
 static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, int64_t ldw, const void* bias,
                          const float* img_bias, int img_bias_ld, int rows_per_img, const void* residual,
                          int64_t res_pix_stride, void* out, int64_t out_pix_stride, int Nimg, int H, int W /*output*/,
-                         int Cout, int ntaps, int stride, int geglu, int force_bn, cudaStream_t stream) {
+                         int Cout, int ntaps, int stride, int geglu, int force_bn, const mvd_gemm_extras* ex,
+                         cudaStream_t stream) {
   const int Cin = a1.C + (a2 ? a2->C : 0);
   MVD_CHECK(Cin % 64 == 0 && a1.C % 64 == 0, "gemm/conv: K (=%d, first source %d) must be a multiple of 64", Cin,
             a1.C);
@@ -600,6 +680,38 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   const int BN = pl.bn;
   g.tiles_n = (Cout + BN - 1) / BN;
   g.tiles_total = g.tiles_n * tiles_m;
+  g.rows_total = W;
+  if (ex != nullptr) {
+    const bool linear_mode = ntaps == 1 && H == 1 && Nimg == 1;
+    if (ex->ln_stats != nullptr) {
+      MVD_CHECK(linear_mode && a2 == nullptr && ex->ln_parts > 0 && ex->ln_colsum != nullptr,
+                "gemm: the LayerNorm fold needs a single-source linear, ln_parts > 0 and column sums");
+      MVD_CHECK(geglu || (img_bias != nullptr && bias == nullptr),
+                "gemm: with the LayerNorm fold the constant term (W.beta + bias) is passed as the fp32 row-group bias");
+      MVD_CHECK(((reinterpret_cast<uintptr_t>(ex->ln_stats) & 7) | (reinterpret_cast<uintptr_t>(ex->ln_colsum) & 15)) == 0,
+                "gemm: ln_stats must be 8-byte and ln_colsum 16-byte aligned");
+      g.ln_stats = reinterpret_cast<const float2*>(ex->ln_stats);
+      g.ln_colsum = ex->ln_colsum;
+      g.ln_parts = ex->ln_parts;
+      g.ln_inv_k = 1.0f / static_cast<float>(Cin);
+      g.ln_eps = ex->ln_eps;
+    }
+    if (ex->stats_out != nullptr) {
+      MVD_CHECK(linear_mode && !geglu, "gemm: row statistics are produced by plain linears only");
+      MVD_CHECK(ex->stats_parts == g.tiles_n, "gemm: stats_out was sized for %d column tiles, this launch has %d "
+                "(ask mvd_gemm_plan)", ex->stats_parts, g.tiles_n);
+      MVD_CHECK((reinterpret_cast<uintptr_t>(ex->stats_out) & 7) == 0, "gemm: stats_out must be 8-byte aligned");
+      g.stats_out = reinterpret_cast<float2*>(ex->stats_out);
+    }
+    if (ex->film_scale != nullptr) {
+      MVD_CHECK(!geglu && ex->film_shift != nullptr && ex->film_ld % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(ex->film_scale) | reinterpret_cast<uintptr_t>(ex->film_shift)) & 15) == 0,
+                "gemm: FiLM needs 16-byte aligned fp32 scale and shift rows with a stride multiple of 4");
+      g.film_scale = ex->film_scale;
+      g.film_shift = ex->film_shift;
+      g.film_ld = ex->film_ld;
+    }
+  }
 
   CUtensorMap mA, mA2, mB, mO, mR;
   // --- A maps
@@ -704,22 +816,30 @@ int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntap
   return MVD_OK;
 }
 
-int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
-                    int64_t ldw, const void* bias, const float* row_group_bias, int row_group_bias_ld,
-                    int rows_per_group, const void* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
-                    int geglu, int tile_n, void* stream) {
+int mvd_linear_ex_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
+                       int64_t ldw, const void* bias, const float* row_group_bias, int row_group_bias_ld,
+                       int rows_per_group, const void* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
+                       int geglu, int tile_n, const mvd_gemm_extras* extras, void* stream) {
   using namespace mvd;
   MVD_CHECK(M > 0 && N > 0 && k1 > 0, "linear: empty problem M=%d N=%d K=%d", M, N, k1);
   OperandA s1{a, k1, lda};
   OperandA s2{a2, k2, lda2};
   return run_gemm_conv(s1, (a2 && k2 > 0) ? &s2 : nullptr, w, ldw, bias, row_group_bias, row_group_bias_ld,
                        rows_per_group, residual, ldr, out, ldo, /*Nimg=*/1, /*H=*/1, /*W=*/M, N, /*ntaps=*/1,
-                       /*stride=*/1, geglu, tile_n, static_cast<cudaStream_t>(stream));
+                       /*stride=*/1, geglu, tile_n, extras, static_cast<cudaStream_t>(stream));
 }
 
-int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
-                     const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
-                     int w_out, int c_out, int stride, int tile_n, void* stream) {
+int mvd_linear_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
+                    int64_t ldw, const void* bias, const float* row_group_bias, int row_group_bias_ld,
+                    int rows_per_group, const void* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,
+                    int geglu, int tile_n, void* stream) {
+  return mvd_linear_ex_bf16(a, lda, k1, a2, lda2, k2, w, ldw, bias, row_group_bias, row_group_bias_ld, rows_per_group,
+                            residual, ldr, out, ldo, M, N, geglu, tile_n, nullptr, stream);
+}
+
+int mvd_conv3x3_ex_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
+                        const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
+                        int w_out, int c_out, int stride, int tile_n, const mvd_gemm_extras* extras, void* stream) {
   using namespace mvd;
   MVD_CHECK(n_img > 0 && h_out > 0 && w_out > 0, "conv3x3: empty problem");
   MVD_CHECK(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
@@ -727,8 +847,15 @@ int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const vo
   OperandA s2{x2, cin2, cin2};
   const int cin = cin1 + ((x2 && cin2 > 0) ? cin2 : 0);
   return run_gemm_conv(s1, (x2 && cin2 > 0) ? &s2 : nullptr, w, static_cast<int64_t>(9) * cin, bias, img_bias,
-                       img_bias_ld > 0 ? img_bias_ld : c_out, /*rows_per_group=*/0, residual, c_out, out, c_out, n_img, h_out, w_out, c_out, /*ntaps=*/9,
-                       stride, /*geglu=*/0, tile_n, static_cast<cudaStream_t>(stream));
+                       img_bias_ld, /*rows_per_group=*/0, residual, c_out, out, c_out, n_img, h_out, w_out, c_out,
+                       /*ntaps=*/9, stride, /*geglu=*/0, tile_n, extras, static_cast<cudaStream_t>(stream));
+}
+
+int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const void* w, const void* bias,
+                     const float* img_bias, int img_bias_ld, const void* residual, void* out, int n_img, int h_out,
+                     int w_out, int c_out, int stride, int tile_n, void* stream) {
+  return mvd_conv3x3_ex_bf16(x, cin1, x2, cin2, w, bias, img_bias, img_bias_ld, residual, out, n_img, h_out, w_out,
+                             c_out, stride, tile_n, nullptr, stream);
 }
 
 }  // extern "C"

@@ -55,10 +55,10 @@ def install_cfg_pair_exchange(sess, plan: Dict, guidance: float):
     gathered = torch.empty((cfg,) + tuple(sess.latents.shape), device=sess.latents.device, dtype=torch.float32)
 
     def step():
-        out = sess.unet(sample=sess.latents, timestep=sess.t_dev, encoder_hidden_states=sess.text, **sess.extra).sample
+        out = sess.forward_unet(sess.latents)
         dist.all_gather_into_tensor(gathered, out.contiguous(), group=group)
         ops.cfg_ddpm_step_table(gathered, sess.latents, sess.noise_table, cfg, guidance, sess.coef, sess.step_idx)
-        ops.advance_step(sess.step_idx, sess.coef, sess.t_dev)
+        sess.advance()
 
     sess._eager_step = step
     sess.guidance = guidance

@@ -26,7 +26,12 @@ from .attention import get_attention_processor_for_module
 from .camera_encoder import CameraEncoder
 from .image_encoder import ImageEncoder
 from .scheduler import DDPMScheduler, ShiftSNRScheduler
+import os
+
 from .unet import BF16, UNet2DConditionModel, _small_linear_any_m, nhwc_view, nchw_shape
+
+# apply the camera FiLM of the up blocks in the epilogue of the block's last GEMM / conv (MVD_FUSE_FILM=0: film kernel)
+FUSE_UP_FILM = os.environ.get("MVD_FUSE_FILM", "1") != "0"
 
 
 class UNetOutput(NamedTuple):
@@ -80,6 +85,7 @@ class MultiViewUNet(nn.Module):
         self.current_camera_embedding = None
         # multi-GPU view sharding (mvd_b200/dist.py): dict(view0, views_local, views_total[, cfg_total, ie_text])
         self.shard = None
+        self.fuse_up_film = FUSE_UP_FILM  # camera FiLM of the up blocks applied in the block's last epilogue
         self._init_image_cross_attention()
         super().to(dtype=dtype)
 
@@ -143,6 +149,14 @@ class MultiViewUNet(nn.Module):
             # "output" modulator on the input latents (mvd_unet.py:256-258): fused into conv_in
             mod = self.camera_encoder.modulation("output", self.current_camera_embedding)
             self.base_unet.input_film = (mod, float(self.camera_encoder.modulation_strength))
+        # up blocks return only their output, so its FiLM is applied by the block's last kernel (conv / proj_out
+        # epilogue) instead of a separate pass; down blocks also hand the UNMODULATED tensor to the skip stack
+        # (camera_encoder.py:201-205), so theirs stays a kernel of its own
+        for i, blk in enumerate(self.base_unet.up_blocks):
+            blk.out_film = None
+            if self.fuse_up_film and self.current_camera_embedding is not None:
+                blk.out_film = self.camera_encoder.film_coefficients(f"up_{i}", self.current_camera_embedding,
+                                                                     sample.shape[0])
 
         ref_hidden_states = None
         ref_batch_index = None
@@ -283,6 +297,9 @@ class MultiViewUNet(nn.Module):
         if register and not self.hooks:
             def get_hook(idx, direction):
                 def hook(module, inputs, output):
+                    if getattr(module, "film_applied", False):  # already applied in the block's last epilogue
+                        module.film_applied = False
+                        return output
                     if self.current_camera_embedding is not None:
                         return self.camera_encoder.apply_modulation(output, f"{direction}_{idx}",
                                                                     self.current_camera_embedding)

@@ -6,6 +6,7 @@ or CPU fallback.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional
 
@@ -38,6 +39,73 @@ def _rows2d(t: torch.Tensor, name: str):
     return t.data_ptr(), t.stride(0), t.shape[0], t.shape[1]
 
 
+class _GemmExtras(ctypes.Structure):  # mirrors mvd_gemm_extras (include/mvd_b200.h)
+    _fields_ = [("ln_stats", ctypes.c_void_p), ("ln_colsum", ctypes.c_void_p), ("ln_parts", ctypes.c_int),
+                ("ln_eps", ctypes.c_float), ("stats_out", ctypes.c_void_p), ("stats_parts", ctypes.c_int),
+                ("film_scale", ctypes.c_void_p), ("film_shift", ctypes.c_void_p), ("film_ld", ctypes.c_int)]
+
+
+class RowStats:
+    """Partial (sum, sum of squares) of every row of a [M, C] bf16 activation, one pair per column tile of the launch
+    that produced it: what the LayerNorm folded into the NEXT GEMM needs (buf: fp32 [M, parts, 2])."""
+
+    __slots__ = ("buf", "parts", "channels")
+
+    def __init__(self, buf: torch.Tensor, parts: int, channels: int):
+        self.buf, self.parts, self.channels = buf, parts, channels
+
+
+class LNFold:
+    """LayerNorm(x) @ W^T folded into one GEMM on the raw x: `stats` of x, `colsum[n]` = sum_k of the gamma-scaled bf16
+    weight row n (fp32); the caller's weight carries gamma and its bias carries W.beta."""
+
+    __slots__ = ("stats", "colsum", "eps")
+
+    def __init__(self, stats: RowStats, colsum: torch.Tensor, eps: float):
+        self.stats, self.colsum, self.eps = stats, colsum, float(eps)
+
+
+_PLAN_CACHE: dict = {}
+
+
+def linear_column_tiles(M: int, N: int, K: int, geglu: bool = False, tile_n: int = 0) -> int:
+    """Column-tile count of the mvd_linear launch for this problem (mvd_gemm_plan): the `parts` of its RowStats."""
+    key = (M, N, K, geglu, tile_n)
+    got = _PLAN_CACHE.get(key)
+    if got is None:
+        bn = ctypes.c_int()
+        check(lib().mvd_gemm_plan(1, 1, M, K, N, 1, 1, int(geglu), tile_n, ctypes.byref(bn), None, None),
+              "mvd_gemm_plan")
+        got = (N + bn.value - 1) // bn.value
+        _PLAN_CACHE[key] = got
+    return got
+
+
+def _extras(ln: Optional["LNFold"], stats: Optional["RowStats"], film, N: int, M: int):
+    if ln is None and stats is None and film is None:
+        return None, ()
+    ex = _GemmExtras()
+    keep = []
+    if ln is not None:
+        _contig(ln.stats.buf, "ln.stats", F32)
+        _contig(ln.colsum, "ln.colsum", F32)
+        if ln.colsum.numel() != N or ln.stats.buf.shape[0] != M:
+            raise ValueError("LayerNorm fold: colsum must be [N] and stats cover the M rows of a")
+        ex.ln_stats, ex.ln_colsum = ln.stats.buf.data_ptr(), ln.colsum.data_ptr()
+        ex.ln_parts, ex.ln_eps = ln.stats.parts, ln.eps
+    if stats is not None:
+        ex.stats_out, ex.stats_parts = stats.buf.data_ptr(), stats.parts
+    if film is not None:
+        scale, shift = film
+        _req(scale, "film scale", F32)
+        _req(shift, "film shift", F32)
+        if scale.shape != shift.shape or scale.dim() != 2 or scale.shape[1] != N or scale.stride(1) != 1 or \
+                shift.stride() != scale.stride():
+            raise ValueError("film = (scale, shift): two fp32 [groups, N] tensors of identical layout")
+        ex.film_scale, ex.film_shift, ex.film_ld = scale.data_ptr(), shift.data_ptr(), scale.stride(0)
+    return ex, keep
+
+
 def linear(
     a: torch.Tensor,
     w: torch.Tensor,
@@ -49,8 +117,14 @@ def linear(
     rows_per_group: int = 0,
     out: Optional[torch.Tensor] = None,
     tile_n: int = 0,
-) -> torch.Tensor:
-    """out[M,N] = [a|a2] @ w^T (+bias) (+row_group_bias[row // rows_per_group]) (+residual); optional GEGLU."""
+    ln: Optional[LNFold] = None,
+    want_stats: bool = False,
+    film=None,
+):
+    """out[M,N] = [a|a2] @ w^T (+bias) (+row_group_bias[row // rows_per_group]) (+residual); optional GEGLU.
+    ln: LayerNorm of a's rows folded in (see LNFold); want_stats: also return the RowStats of `out` for the LayerNorm
+    that follows -> (out, RowStats); film = (scale, shift) fp32 [groups, N]: out = out * scale[g] + shift[g] with
+    g = row // rows_per_group (camera FiLM on a block output)."""
     _req(a, "a")
     _req(w, "w")
     pa, lda, M, k1 = _rows2d(a, "a")
@@ -86,12 +160,19 @@ def linear(
         pg, ldg, _, Ng = _rows2d(row_group_bias, "row_group_bias")
         if Ng != N or rows_per_group <= 0:
             raise ValueError("row_group_bias must be [groups, N] with rows_per_group > 0")
+    stats = None
+    if want_stats:
+        parts = linear_column_tiles(M, N, K, geglu, tile_n)
+        stats = RowStats(torch.empty((M, parts, 2), device=a.device, dtype=F32), parts, n_out)
+    if film is not None and rows_per_group <= 0:
+        raise ValueError("film needs rows_per_group > 0")
+    ex, _keep = _extras(ln, stats, film, N, M)
     check(
-        lib().mvd_linear_bf16(pa, lda, k1, pa2, lda2, k2, pw, ldw, _p(bias), pg, ldg, rows_per_group, pr, ldr, po, ldo,
-                              M, N, int(geglu), tile_n, _stream()),
-        "mvd_linear_bf16",
+        lib().mvd_linear_ex_bf16(pa, lda, k1, pa2, lda2, k2, pw, ldw, _p(bias), pg, ldg, rows_per_group, pr, ldr, po,
+                                 ldo, M, N, int(geglu), tile_n, None if ex is None else ctypes.byref(ex), _stream()),
+        "mvd_linear_ex_bf16",
     )
-    return out
+    return (out, stats) if want_stats else out
 
 
 def conv3x3(
@@ -104,6 +185,7 @@ def conv3x3(
     stride: int = 1,
     out: Optional[torch.Tensor] = None,
     tile_n: int = 0,
+    film=None,
 ) -> torch.Tensor:
     """NHWC 3x3 conv, padding 1. x: [N,H,W,C1] (x2: [N,H,W,C2] concatenated after x); w: [Cout, 9*(C1+C2)]
     in (ky, kx, c) order; img_bias: fp32 [N, Cout]; residual/out: [N,Ho,Wo,Cout]."""
@@ -139,20 +221,27 @@ def conv3x3(
         _req(img_bias, "img_bias", torch.float32)
         if tuple(img_bias.shape) != (n, cout) or img_bias.stride(1) != 1:
             raise ValueError("img_bias must be fp32 [N, Cout] with unit inner stride")
+    ex = None
+    if film is not None:  # camera FiLM of a block output, per image
+        if film[0].shape[0] != n:
+            raise ValueError("film rows must match the image count")
+        ex, _keep = _extras(None, None, film, cout, n)
     check(
-        lib().mvd_conv3x3_bf16(_p(x), c1, _p(x2), c2, _p(w), _p(bias), _p(img_bias),
-                               0 if img_bias is None else img_bias.stride(0), _p(residual), _p(out), n, ho, wo,
-                               cout, stride, tile_n, _stream()),
-        "mvd_conv3x3_bf16",
+        lib().mvd_conv3x3_ex_bf16(_p(x), c1, _p(x2), c2, _p(w), _p(bias), _p(img_bias),
+                                  0 if img_bias is None else img_bias.stride(0), _p(residual), _p(out), n, ho, wo,
+                                  cout, stride, tile_n, None if ex is None else ctypes.byref(ex), _stream()),
+        "mvd_conv3x3_ex_bf16",
     )
     return out
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, scale: Optional[float] = None,
-              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, split_tail: bool = True, co_units: int = 0) -> torch.Tensor:
     """q: [B,Sq,>=heads*64] view, k/v: [B,Skv,...] views (unit inner stride); head h = columns h*64.. .
     k/v may be batch-broadcast views (stride(0) == 0, e.g. `kv.expand(B, -1, -1)`): one K/V sequence shared by all
-    batch entries (cross-view reference mode)."""
+    batch entries (cross-view reference mode).
+    split_tail: let the launch split the units of its last partial wave along S_kv (needs the per-stream workspace);
+    co_units: 256-row units of another attention launch running concurrently on a different stream (see the header)."""
     for t, nme in ((q, "q"), (k, "k"), (v, "v")):
         _req(t, nme)
         if t.dim() != 3 or t.stride(2) != 1 or t.shape[2] != heads * 64:
@@ -168,12 +257,14 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
         raise ValueError("out must be [B,Sq,heads*64] with unit inner stride")
     if scale is None:
         scale = 0.125
-    nbytes = _attn_ws_bytes()
-    ws = _workspace(q.device, nbytes // 4, "attn")  # per (device, stream): the two adapter branches never share one
+    ws_ptr, ws_bytes = None, 0
+    if split_tail:
+        ws = _workspace(q.device, _attn_ws_bytes() // 4, "attn")  # per (device, stream): never shared by the two branches
+        ws_ptr, ws_bytes = ws.data_ptr(), ws.numel() * 4
     check(
         lib().mvd_attention_bf16_ws(q.data_ptr(), q.stride(1), q.stride(0), k.data_ptr(), k.stride(1), k.stride(0),
                                     v.data_ptr(), v.stride(1), v.stride(0), out.data_ptr(), out.stride(1),
-                                    out.stride(0), B, heads, Sq, Skv, float(scale), ws.data_ptr(), ws.numel() * 4,
+                                    out.stride(0), B, heads, Sq, Skv, float(scale), ws_ptr, ws_bytes, int(co_units),
                                     _stream()),
         "mvd_attention_bf16_ws",
     )
@@ -181,6 +272,11 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
 
 
 _ATTN_WS_BYTES = None
+
+
+def attention_units(batch: int, heads: int, s_q: int) -> int:
+    """Scheduling units (256-row tile pair, head, batch) of an attention launch — the `co_units` of its sibling."""
+    return ((s_q + 255) // 256) * heads * batch
 
 
 def _attn_ws_bytes() -> int:
@@ -451,6 +547,21 @@ def advance_step(step_idx: torch.Tensor, coef_table: torch.Tensor, timestep_out:
     _contig(timestep_out, "timestep_out", F32)
     check(lib().mvd_advance_step(_p(step_idx), _p(coef_table), _p(timestep_out), coef_table.shape[0], _stream()),
           "mvd_advance_step")
+
+
+def advance_step_rows(step_idx: torch.Tensor, coef_table: torch.Tensor, timestep_out: torch.Tensor,
+                      row_table: torch.Tensor, row_out: torch.Tensor) -> None:
+    """advance_step + copy of the new step's row of a per-schedule fp32 table [steps, row_len] into row_out."""
+    _contig(step_idx, "step_idx", torch.int32)
+    _contig(coef_table, "coef_table", F32)
+    _contig(timestep_out, "timestep_out", F32)
+    _contig(row_table, "row_table", F32)
+    _contig(row_out, "row_out", F32)
+    if row_table.dim() != 2 or row_table.shape[0] != coef_table.shape[0] or row_out.numel() != row_table.shape[1]:
+        raise ValueError("row_table must be [steps, row_len] and row_out hold row_len floats")
+    check(lib().mvd_advance_step_rows(_p(step_idx), _p(coef_table), _p(timestep_out), coef_table.shape[0],
+                                      _p(row_table), _p(row_out), row_table.shape[1], _stream()),
+          "mvd_advance_step_rows")
 
 
 def kernel_launch_count() -> int:

@@ -165,6 +165,20 @@ class DenoiseSession:
             if with_noise else None
         self.step_idx = torch.zeros(1, device=dev, dtype=torch.int32)
         self.t_dev = torch.full((1,), float(self.timesteps[0]), device=dev, dtype=torch.float32)
+        # Everything that depends on the timestep only (Timesteps + TimestepEmbedding + the 22 time_emb_proj outputs)
+        # is a per-SCHEDULE table, not per-step work: computed here once with the model's own kernels; the step reads
+        # the current row, which advance_step_rows refreshes together with the step counter.
+        base = getattr(self.unet, "base_unet", None)
+        self.temb_table, self.temb_row = None, None
+        if base is not None and hasattr(base, "timestep_rows") and next(base.parameters()).is_cuda:
+            with torch.no_grad():
+                rows = [base.timestep_rows(torch.full((1,), float(t), device=dev, dtype=torch.float32), 1)[1]
+                        for t in self.timesteps]
+            self.temb_table = torch.cat(rows, 0).contiguous()
+            if self.temb_table.shape[1] % 4 == 0:
+                self.temb_row = self.temb_table[0].clone()
+            else:
+                self.temb_table = None
         self.graph = None
         self.use_cuda_graph = use_cuda_graph
         self.launches_per_step = 0
@@ -176,16 +190,36 @@ class DenoiseSession:
             self.noise_table.copy_(variance_noises.reshape(self.n_steps, -1).to(self.noise_table.device), non_blocking=True)
         self.step_idx.zero_()
         self.t_dev.fill_(float(self.timesteps[0]))
+        if self.temb_row is not None:
+            self.temb_row.copy_(self.temb_table[0])
+
+    def forward_unet(self, inp: torch.Tensor) -> torch.Tensor:
+        """The UNet call of the step, with the per-schedule time-embedding row installed for its duration."""
+        base = getattr(self.unet, "base_unet", None)
+        if self.temb_row is not None:
+            base.temb_rows = self.temb_row
+        try:
+            return self.unet(sample=inp, timestep=self.t_dev, encoder_hidden_states=self.text, **self.extra).sample
+        finally:
+            if self.temb_row is not None:
+                base.temb_rows = None
+
+    def advance(self):
+        if self.temb_row is not None:
+            ops.advance_step_rows(self.step_idx, self.coef, self.t_dev, self.temb_table, self.temb_row)
+        else:
+            ops.advance_step(self.step_idx, self.coef, self.t_dev)
 
     def _eager_step(self):
         inp = torch.cat([self.latents] * 2) if self.cfg == 2 else self.latents
-        out = self.unet(sample=inp, timestep=self.t_dev, encoder_hidden_states=self.text, **self.extra).sample
+        out = self.forward_unet(inp)
         ops.cfg_ddpm_step_table(out, self.latents, self.noise_table, self.cfg, self.guidance, self.coef, self.step_idx)
-        ops.advance_step(self.step_idx, self.coef, self.t_dev)
+        self.advance()
 
     def capture(self, warmup: int = 2):
         """Warm every cache (weight packs, reference features, K/V) eagerly, then record one step."""
-        saved = (self.latents.clone(), self.step_idx.clone(), self.t_dev.clone())
+        saved = (self.latents.clone(), self.step_idx.clone(), self.t_dev.clone(),
+                 None if self.temb_row is None else self.temb_row.clone())
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -201,6 +235,8 @@ class DenoiseSession:
         self.latents.copy_(saved[0])
         self.step_idx.copy_(saved[1])
         self.t_dev.copy_(saved[2])
+        if saved[3] is not None:
+            self.temb_row.copy_(saved[3])
         torch.cuda.synchronize()
 
     @torch.no_grad()

@@ -47,6 +47,9 @@ SD21_CONFIG = dict(
 # tile width the GEGLU weight interleave is built for (ops.linear(..., geglu=True, tile_n=...)); 128 only for the
 # experimental weight-stationary GEMM tiles (MVD_GEMM_WS=1), which are 128 wide
 GEGLU_TILE = 128 if os.environ.get("MVD_GEGLU_TILE", "256") == "128" else 256
+# fold the three LayerNorms of a transformer block into the GEMMs that consume them (MVD_FOLD_LN=0: LayerNorm kernels)
+FOLD_LAYERNORM = os.environ.get("MVD_FOLD_LN", "1") != "0"
+FOLD_GEGLU_MAX_ROWS = int(os.environ.get("MVD_FOLD_GEGLU_MAX_ROWS", "4096"))
 
 
 class _Config(dict):
@@ -121,6 +124,29 @@ def _bf16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     if t is None:
         return None
     return t.detach().to(BF16).contiguous()
+
+
+class LNInput:
+    """A LayerNorm to be folded into the GEMM that consumes it: the module (gamma, beta, eps) + the row statistics of
+    the raw activation, produced by the epilogue of the launch that wrote it (ops.RowStats)."""
+
+    __slots__ = ("norm", "stats")
+
+    def __init__(self, norm: nn.LayerNorm, stats):
+        self.norm, self.stats = norm, stats
+
+
+def fold_layernorm(w: torch.Tensor, norm: nn.LayerNorm, bias: Optional[torch.Tensor] = None):
+    """LayerNorm(x) @ w^T + bias  ==  rstd * (x @ wg^T - mean * colsum) + c   with
+    wg = w * gamma (per input channel, rounded to bf16 — what the MMA multiplies), colsum[n] = sum_k wg[n, k],
+    c = w @ beta + bias. Returns (wg bf16 [N, K], colsum fp32 [N], c fp32 [1, N])."""
+    wf = w.detach().float()
+    wg = (wf * norm.weight.detach().float()[None, :]).to(BF16).contiguous()
+    colsum = wg.float().sum(1).contiguous()
+    c = wf @ norm.bias.detach().float()
+    if bias is not None:
+        c = c + bias.detach().float()
+    return wg, colsum, c.view(1, -1).contiguous()
 
 
 def conv3x3_weight(w: torch.Tensor) -> torch.Tensor:
@@ -215,22 +241,35 @@ class AttnProcessor2_0:
     to_out(SDPA(to_q h, to_k e, to_v e)). Fused QKV projection, in-place head slicing, optional fused residual."""
 
     def __call__(self, attn: "Attention", hidden_states: torch.Tensor, encoder_hidden_states=None,
-                 attention_mask=None, temb=None, residual: Optional[torch.Tensor] = None, *args, **kwargs):
+                 attention_mask=None, temb=None, residual: Optional[torch.Tensor] = None,
+                 ln_fold: Optional[LNInput] = None, want_stats: bool = False, *args, **kwargs):
+        """ln_fold: hidden_states is the RAW residual stream and the block's LayerNorm is folded into the input
+        projection (LNInput); want_stats: also return the ops.RowStats of the result (for the next LayerNorm)."""
         if attention_mask is not None:
             raise NotImplementedError("attention masks are not on MVD's hot path")
         b, s, c = hidden_states.shape
         pk = attn.pack()
         hs2d = hidden_states.reshape(b * s, c)
+        w_in = pk["wqkv"] if encoder_hidden_states is None else pk["wq"]
+        if ln_fold is not None:
+            wg, colsum, cst = attn.ln_pack(ln_fold.norm, "wqkv" if encoder_hidden_states is None else "wq")
+            proj = ops.linear(hs2d, wg, row_group_bias=cst, rows_per_group=b * s,
+                              ln=ops.LNFold(ln_fold.stats, colsum, ln_fold.norm.eps))
+        else:
+            proj = ops.linear(hs2d, w_in)
         if encoder_hidden_states is None:
-            qkv = ops.linear(hs2d, pk["wqkv"]).view(b, s, 3 * c)
+            qkv = proj.view(b, s, 3 * c)
             q, k, v = qkv[:, :, :c], qkv[:, :, c:2 * c], qkv[:, :, 2 * c:]
         else:
-            q = ops.linear(hs2d, pk["wq"]).view(b, s, c)
+            q = proj.view(b, s, c)
             kv = attn.context_kv(encoder_hidden_states)
             k, v = kv[:, :, :c], kv[:, :, c:]
         o = ops.attention(q, k, v, attn.heads, attn.scale)
         res2d = residual.reshape(b * s, c) if residual is not None else None
-        return ops.linear(o.view(b * s, c), pk["wo"], bias=pk["bo"], residual=res2d).view(b, s, c)
+        out = ops.linear(o.view(b * s, c), pk["wo"], bias=pk["bo"], residual=res2d, want_stats=want_stats)
+        if want_stats:
+            return out[0].view(b, s, c), out[1]
+        return out.view(b, s, c)
 
 
 class Attention(PackedModule):
@@ -258,6 +297,18 @@ class Attention(PackedModule):
             p["wqkv"] = _bf16(torch.cat([self.to_q.weight, self.to_k.weight, self.to_v.weight], 0))
         self.__dict__["_ctx_cache"] = None
         return p
+
+    def ln_pack(self, norm: nn.LayerNorm, which: str):
+        """(gamma-scaled weight, column sums, W.beta) of the input projection `which` for a preceding LayerNorm."""
+        pk = self.pack()
+        key = (which, _versions(*self._pack_params(), norm.weight, norm.bias))
+        cache = self.__dict__.setdefault("_ln_cache", {})
+        hit = cache.get(which)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, fold_layernorm(pk[which], norm))
+            cache[which] = hit
+        return hit[1]
 
     def context_kv(self, ctx: torch.Tensor) -> torch.Tensor:
         """[B, S_ctx, 2C] = [to_k(ctx) | to_v(ctx)]; cached while the same context tensor is passed (text
@@ -309,9 +360,27 @@ class FeedForward(PackedModule):
         return dict(w1=_bf16(wp.reshape(2 * inner, -1)), b1=_bf16(bp.reshape(-1)), w2=_bf16(self.net[2].weight),
                     b2=_bf16(self.net[2].bias))
 
-    def forward(self, x2d: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def ln_pack(self, norm: nn.LayerNorm):
         p = self.pack()
-        h = ops.linear(x2d, p["w1"], bias=p["b1"], geglu=True, tile_n=GEGLU_TILE)
+        key = _versions(*self._pack_params(), norm.weight, norm.bias)
+        hit = self.__dict__.get("_ln_cache")
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                wg, colsum, cst = fold_layernorm(p["w1"], norm, p["b1"])  # rows already in the GEGLU interleave
+                hit = (key, (wg, colsum, _bf16(cst.view(-1))))
+            self.__dict__["_ln_cache"] = hit
+        return hit[1]
+
+    def forward(self, x2d: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                ln_fold: Optional[LNInput] = None) -> torch.Tensor:
+        """ln_fold: x2d is the raw residual stream, norm3 is folded into the GEGLU projection."""
+        p = self.pack()
+        if ln_fold is not None:
+            wg, colsum, b1 = self.ln_pack(ln_fold.norm)
+            h = ops.linear(x2d, wg, bias=b1, geglu=True, tile_n=GEGLU_TILE,
+                           ln=ops.LNFold(ln_fold.stats, colsum, ln_fold.norm.eps))
+        else:
+            h = ops.linear(x2d, p["w1"], bias=p["b1"], geglu=True, tile_n=GEGLU_TILE)
         return ops.linear(h, p["w2"], bias=p["b2"], residual=residual)
 
 
@@ -336,9 +405,35 @@ class BasicTransformerBlock(nn.Module):
             return attn(normed, encoder_hidden_states=ctx, residual=h, **kw)
         return ops.add(h, attn(normed, encoder_hidden_states=ctx, **kw).contiguous())
 
-    def forward(self, h: torch.Tensor, encoder_hidden_states=None, cross_attention_kwargs=None) -> torch.Tensor:
+    def can_fold_layernorm(self) -> bool:
+        """Both processors take the raw stream + an LNInput (ours do; a foreign processor gets explicit LayerNorms)."""
+        return FOLD_LAYERNORM and all({"ln_fold", "want_stats", "residual"} <= accepted_params(a.processor)
+                                      for a in (self.attn1, self.attn2))
+
+    def forward(self, h: torch.Tensor, encoder_hidden_states=None, cross_attention_kwargs=None,
+                h_stats=None) -> torch.Tensor:
+        """h_stats: ops.RowStats of h from the launch that produced it. With it the three LayerNorms never run as
+        kernels: each is folded into the projection that consumes it, and every producing GEMM hands the row
+        statistics of its output to the next one (diffusers BasicTransformerBlock)."""
         kw = dict(cross_attention_kwargs or {})
         b, s, c = h.shape
+        if h_stats is not None and self.can_fold_layernorm():
+            st = h_stats
+            fold_ff = b * s <= FOLD_GEGLU_MAX_ROWS
+            for attn, norm, ctx, want in ((self.attn1, self.norm1, None, True),
+                                          (self.attn2, self.norm2, encoder_hidden_states, fold_ff)):
+                if st is not None:
+                    r = attn(h, encoder_hidden_states=ctx, residual=h, ln_fold=LNInput(norm, st), want_stats=want, **kw)
+                else:  # the processor could not hand statistics on (foreign original processor): explicit LayerNorm
+                    r = attn(self._ln(norm, h), encoder_hidden_states=ctx, residual=h, want_stats=want, **kw)
+                h, st = r if want else (r, None)
+            h2d = h.view(b * s, c)
+            # The GEGLU projection is bound by its epilogue (erf GELU on 8C columns); measured in round 2
+            # (profiles/r2_ln_fold.txt): with many rows the fold costs it more (+29 us at 32768 x 320) than the
+            # LayerNorm kernel it removes (14 us), with few rows the launch is what counts.
+            if st is not None and fold_ff:
+                return self.ff(h2d, residual=h2d, ln_fold=LNInput(self.norm3, st)).view(b, s, c)
+            return self.ff(self._ln(self.norm3, h).view(b * s, c), residual=h2d).view(b, s, c)
         h = self._attend(self.attn1, self._ln(self.norm1, h), h, None, kw)
         h = self._attend(self.attn2, self._ln(self.norm2, h), h, encoder_hidden_states, kw)
         n3 = self._ln(self.norm3, h)
@@ -354,17 +449,22 @@ class Transformer2DModel(nn.Module):
         self.transformer_blocks = nn.ModuleList([BasicTransformerBlock(dim, heads, cross_dim)])
         self.proj_out = nn.Linear(dim, dim)
 
-    def forward(self, x, encoder_hidden_states=None, cross_attention_kwargs=None, return_dict=False):
+    def forward(self, x, encoder_hidden_states=None, cross_attention_kwargs=None, return_dict=False, out_film=None):
+        """out_film = (scale, shift) fp32 [B, C]: camera FiLM of the enclosing block's output, applied in proj_out's
+        epilogue (after the residual)."""
         xa = nhwc_view(x)
         n, hh, ww, c = xa.shape
         res2d = xa.reshape(n * hh * ww, c)
         h = ops.groupnorm(xa, _bf16(self.norm.weight), _bf16(self.norm.bias), self.groups, self.norm.eps, silu=False)
-        h = ops.linear(h.view(n * hh * ww, c), _bf16(self.proj_in.weight), bias=_bf16(self.proj_in.bias))
+        fold = len(self.transformer_blocks) == 1 and self.transformer_blocks[0].can_fold_layernorm()
+        h = ops.linear(h.view(n * hh * ww, c), _bf16(self.proj_in.weight), bias=_bf16(self.proj_in.bias),
+                       want_stats=fold)
+        h, h_stats = h if fold else (h, None)
         h = h.view(n, hh * ww, c)
         for blk in self.transformer_blocks:
-            h = blk(h, encoder_hidden_states, cross_attention_kwargs)
+            h = blk(h, encoder_hidden_states, cross_attention_kwargs, h_stats=h_stats)
         out = ops.linear(h.view(n * hh * ww, c), _bf16(self.proj_out.weight), bias=_bf16(self.proj_out.bias),
-                         residual=res2d)
+                         residual=res2d, rows_per_group=hh * ww if out_film is not None else 0, film=out_film)
         return (nchw_shape(out.view(n, hh, ww, c)),)
 
 
@@ -391,9 +491,10 @@ class Upsample2D(_PackedConv):
         super().__init__()
         self.conv = nn.Conv2d(c, c, 3, padding=1)
 
-    def forward(self, x):
+    def forward(self, x, film=None):
+        """film = (scale, shift) fp32 [B, C]: camera FiLM of the block output, applied in the conv epilogue."""
         p = self.pack()
-        return nchw_shape(ops.conv3x3(ops.upsample2x(nhwc_view(x)), p["w"], bias=p["b"]))
+        return nchw_shape(ops.conv3x3(ops.upsample2x(nhwc_view(x)), p["w"], bias=p["b"], film=film))
 
 
 class DownBlock(nn.Module):
@@ -450,15 +551,25 @@ class UpBlock(nn.Module):
             self.attentions = nn.ModuleList([Transformer2DModel(cout, heads, cross_dim) for _ in range(3)])
         self.upsamplers = nn.ModuleList([Upsample2D(cout)]) if add_up else None
         self.has_attn = has_attn
+        # camera FiLM of this block's output (MultiViewUNet sets it per forward): (scale, shift) fp32 [B, C]; when the
+        # block's last op can apply it in its epilogue, `film_applied` tells the forward hook not to do it again
+        self.out_film = None
+        self.film_applied = False
 
     def forward(self, h, skips, temb, encoder_hidden_states=None, cross_attention_kwargs=None, temb_projs=None):
+        film, self.film_applied = self.out_film, False
+        n_res = len(self.resnets)
         for i, res in enumerate(self.resnets):
             skip, skips = skips[-1], skips[:-1]
             h = res(h, temb, skip=skip, temb_proj=None if temb_projs is None else temb_projs[id(res)])
             if self.has_attn:
-                h = self.attentions[i](h, encoder_hidden_states, cross_attention_kwargs)[0]
+                last = film is not None and i == n_res - 1 and self.upsamplers is None
+                h = self.attentions[i](h, encoder_hidden_states, cross_attention_kwargs,
+                                       out_film=film if last else None)[0]
+                self.film_applied = self.film_applied or last
         if self.upsamplers is not None:
-            h = self.upsamplers[0](h)
+            h = self.upsamplers[0](h, film=film)
+            self.film_applied = film is not None
         return h
 
 
@@ -497,6 +608,7 @@ class UNet2DConditionModel(PackedModule):
         self.conv_act = nn.SiLU()
         self.conv_out = nn.Conv2d(ch[0], cfg["out_channels"], 3, padding=1)
         self.input_film = None  # (mod fp32 [V,8], strength): camera FiLM on the input latents, fused into conv_in
+        self.temb_rows = None   # fp32 [sum of resnet out_channels]: the current row of a DenoiseSession's per-schedule table
 
     @property
     def device(self):
@@ -534,6 +646,13 @@ class UNet2DConditionModel(PackedModule):
             tb=_bf16(torch.cat([r.time_emb_proj.bias for r in res], 0)), toffs=offs,
         )
 
+    def timestep_rows(self, t: torch.Tensor, bsz: int):
+        """diffusers Timesteps + TimestepEmbedding, then all 22 time_emb_proj(SiLU(temb)) as one skinny GEMM:
+        (temb fp32 [bsz, 1280], rows fp32 [bsz, sum of resnet out_channels])."""
+        p = self.pack()
+        temb = self.time_embedding(ops.timestep_embedding(t, bsz, self.config.block_out_channels[0]))
+        return temb, _small_linear_any_m(temb, p["tw"], p["tb"], silu_in=True)
+
     def forward(self, sample, timestep, encoder_hidden_states, return_dict: bool = True, timestep_cond=None,
                 cross_attention_kwargs: Optional[Dict[str, Any]] = None, added_cond_kwargs=None):
         """sample: fp32 (or bf16) NCHW latents [B,4,H,W]; timestep: python number or tensor (scalar or [B]);
@@ -547,8 +666,13 @@ class UNet2DConditionModel(PackedModule):
             t = timestep.to(device=dev, dtype=torch.float32).reshape(-1).contiguous()
         else:
             t = torch.full((1,), float(timestep), device=dev, dtype=torch.float32)
-        temb = self.time_embedding(ops.timestep_embedding(t, bsz, self.config.block_out_channels[0]))
-        tp_all = _small_linear_any_m(temb, p["tw"], p["tb"], silu_in=True)
+        rows = getattr(self, "temb_rows", None)
+        if rows is not None:
+            # per-schedule table (DenoiseSession): the current step's time_emb_proj outputs, identical for every
+            # sample of the batch (stride-0 rows), no timestep arithmetic in the step
+            temb, tp_all = None, rows.view(1, -1).expand(bsz, -1)
+        else:
+            temb, tp_all = self.timestep_rows(t, bsz)
         temb_projs = {k: tp_all[:, a:b] for k, (a, b) in p["toffs"].items()}
 
         lat = sample.float().contiguous() if sample.dtype != torch.float32 or not sample.is_contiguous() else sample

@@ -30,7 +30,7 @@ def main(path):
     print()
     big = defaultdict(lambda: [0, 0.0])
     for n, g, b, ns in rows:
-        if "gemm_conv" in n or "attn_fwd" in n:
+        if "gemm_conv" in n or "attn_" in n:
             big[(n[:40], g)][0] += 1
             big[(n[:40], g)][1] += ns
     print("largest (kernel, grid) groups:")

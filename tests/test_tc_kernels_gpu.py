@@ -85,6 +85,80 @@ def test_linear_geglu(tile_n):
     _cmp(out, ref, f"geglu bn={tile_n}", atol=3e-2)
 
 
+@pytest.mark.parametrize("M,C,N", [(4096, 320, 1280), (1000, 640, 640), (512, 1280, 320)])
+def test_linear_row_stats_and_layernorm_fold(M, C, N):
+    """Producer epilogue: per-row partial (sum, sum of squares) of the bf16 output, one pair per column tile.
+    Consumer: LayerNorm folded into the GEMM (gamma in the weights, mean / rstd applied in the epilogue) against
+    F.layer_norm followed by the matmul in fp32 — for a plain linear and for the GEGLU projection."""
+    from mvd_b200 import ops
+    from mvd_b200.unet import fold_layernorm
+
+    a = _randn(M, C, seed=1)
+    w0 = _randn(C, C, scale=C ** -0.5, seed=2)
+    b0 = _randn(C, seed=3)
+    r = _randn(M, C, scale=2.0, seed=4) + 1.5          # a residual stream with a clear mean
+    x, st = ops.linear(a, w0, bias=b0, residual=r, want_stats=True)
+    torch.cuda.synchronize()
+    xs = x.float()
+    got = st.buf.sum(1)
+    assert st.buf.shape == (M, st.parts, 2)
+    assert torch.allclose(got[:, 0], xs.sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(got[:, 1], (xs * xs).sum(1), rtol=1e-4, atol=1e-2)
+
+    norm = torch.nn.LayerNorm(C).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(1.0 + 0.3 * torch.randn(C, device="cuda"))
+        norm.bias.copy_(0.2 * torch.randn(C, device="cuda"))
+        norm.weight.copy_(norm.weight.to(torch.bfloat16).float())
+        norm.bias.copy_(norm.bias.to(torch.bfloat16).float())
+    w = _randn(N, C, scale=C ** -0.5, seed=5)
+    ref = F.layer_norm(xs, (C,), norm.weight, norm.bias, norm.eps) @ w.float().t()
+    wg, colsum, cst = fold_layernorm(w, norm)
+    out = ops.linear(x, wg, row_group_bias=cst, rows_per_group=M, ln=ops.LNFold(st, colsum, norm.eps))
+    _cmp(out, ref, f"layernorm fold {M}x{C}->{N}", atol=3e-2)
+    # the un-fused path on the same inputs, for scale: LayerNorm kernel + GEMM
+    unf = ops.linear(ops.layernorm(x, norm.weight.to(torch.bfloat16), norm.bias.to(torch.bfloat16), norm.eps), w)
+    e_f, e_u = (out.float() - ref).abs().max().item(), (unf.float() - ref).abs().max().item()
+    print(f"  max|err| folded {e_f:.3e}  un-fused {e_u:.3e}")
+    assert e_f <= 2.0 * e_u + 1e-2
+
+    # GEGLU projection with the fold (interleaved [value | gate] rows per 256-column tile)
+    inner, half = 4 * C, 128
+    wf = _randn(2 * inner, C, scale=C ** -0.5, seed=6)
+    bf = _randn(2 * inner, seed=7)
+    hh = F.layer_norm(xs, (C,), norm.weight, norm.bias, norm.eps) @ wf.float().t() + bf.float()
+    ref_g = hh[:, :inner] * F.gelu(hh[:, inner:])
+    wp = torch.cat([wf[:inner].view(-1, half, C), wf[inner:].view(-1, half, C)], 1).reshape(2 * inner, C).contiguous()
+    bp = torch.cat([bf[:inner].view(-1, half), bf[inner:].view(-1, half)], 1).reshape(-1).contiguous()
+    wg, colsum, cst = fold_layernorm(wp, norm, bp)
+    out_g = ops.linear(x, wg, bias=cst.view(-1).to(torch.bfloat16), geglu=True, tile_n=256,
+                       ln=ops.LNFold(st, colsum, norm.eps))
+    _cmp(out_g, ref_g, f"layernorm fold + geglu {M}x{C}", atol=8e-2)
+
+
+def test_film_epilogue_linear_and_conv():
+    """out * scale[g] + shift[g] fused behind bias / residual: per row group (linear) and per image (conv)."""
+    from mvd_b200 import ops
+
+    n, hw, c = 4, 16, 320
+    a = _randn(n * hw * hw, c, seed=1)
+    w = _randn(c, c, scale=c ** -0.5, seed=2)
+    b = _randn(c, seed=3)
+    r = _randn(n * hw * hw, c, seed=4)
+    scale = 1.0 + 0.5 * torch.randn(n, c, device="cuda")
+    shift = 0.3 * torch.randn(n, c, device="cuda")
+    ref = (a.float() @ w.float().t() + b.float() + r.float()).view(n, hw * hw, c) * scale[:, None] + shift[:, None]
+    out = ops.linear(a, w, bias=b, residual=r, rows_per_group=hw * hw, film=(scale, shift))
+    _cmp(out, ref.view(-1, c), "linear + film", atol=4e-2)
+    x = _randn(n, hw, hw, c, seed=5)
+    w9 = _randn(c, 9 * c, scale=(9 * c) ** -0.5, seed=6)
+    refc = _conv_ref(x, w9, b, None, r.view(n, hw, hw, c), 1) * scale[:, None, None] + shift[:, None, None]
+    outc = ops.conv3x3(x, w9, bias=b, residual=r.view(n, hw, hw, c), film=(scale, shift))
+    _cmp(outc, refc, "conv + film", atol=4e-2)
+    outs = ops.conv3x3(x, w9, bias=b, stride=2, film=(scale, shift))
+    _cmp(outs, _conv_ref(x, w9, b, None, None, 2) * scale[:, None, None] + shift[:, None, None], "conv s2 + film", atol=4e-2)
+
+
 def _conv_ref(x, w9, bias, img_bias, residual, stride, x2=None):
     xin = x.float() if x2 is None else torch.cat([x.float(), x2.float()], -1)
     cin = xin.shape[-1]
