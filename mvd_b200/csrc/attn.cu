@@ -531,6 +531,13 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     const uint32_t t_o = tmem_base + tm2_o(t) + lane_off;
     const bool tracer = TRACE && blockIdx.x == 0 && q == 0 && lane == 0;
     long long* tr = trace + t * 8 * 64;
+    // CTA-level stamps of the LAST CTA of the grid (a KV part when the tail is split): trace[1024 + i]
+    const bool tracer2 = TRACE && blockIdx.x == gridDim.x - 1 && warp == 4 && lane == 0;
+    if (tracer2) {
+      trace[1024] = clock64();
+      trace[1030] = n_blocks;
+      trace[1031] = nparts;
+    }
     float m_ref = -INFINITY;  // reference maximum (scaled, log2 domain) the exponentials are relative to
     float l = 0.f;            // running sum of exp2(x - m_ref)
 
@@ -637,8 +644,10 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     }
 
     // ---- epilogue
+    if (tracer2) trace[1025] = clock64();
     mbar_wait(o_final, 0);
     tc_fence_after();
+    if (tracer2) trace[1026] = clock64();
     float o[ATT_D];
     {
       uint32_t* orr = reinterpret_cast<uint32_t*>(o);
@@ -651,12 +660,15 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
     if (nparts > 1) {
       // publish this part, take a ticket; the CTA that takes the last one merges all parts of the unit
       const int su = unit - sc.n_full;
-      const size_t slot_row = (static_cast<size_t>(su) * nparts + part) * 256 + row_in_unit;
-      float4* wo = reinterpret_cast<float4*>(sc.ws_o + slot_row * ATT_D);
+      // partial O is stored column-chunk major, [slot][16 float4 chunks][256 rows], so that the 32 rows of a warp
+      // write (and the merging CTA reads) 512 contiguous bytes per instruction
+      const size_t slot = static_cast<size_t>(su) * nparts + part;
+      float4* wo = reinterpret_cast<float4*>(sc.ws_o) + slot * (16 * 256) + row_in_unit;
 #pragma unroll
-      for (int c = 0; c < ATT_D / 4; ++c) wo[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
-      *reinterpret_cast<float2*>(sc.ws_ml + slot_row * 2) = make_float2(m_ref, l);
+      for (int c = 0; c < ATT_D / 4; ++c) wo[c * 256] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      reinterpret_cast<float2*>(sc.ws_ml)[slot * 256 + row_in_unit] = make_float2(m_ref, l);
       __threadfence();
+      if (tracer2) trace[1027] = clock64();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (threadIdx.x == 128) {
         const unsigned int old = atomicAdd(sc.ws_cnt + su, 1u);
@@ -668,29 +680,41 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
       store = *last_flag != 0u;
       if (store) {
         __threadfence();
-        const size_t row0 = static_cast<size_t>(su) * nparts * 256 + row_in_unit;
+        const size_t slot0 = static_cast<size_t>(su) * nparts;
+        const float2* mlp = reinterpret_cast<const float2*>(sc.ws_ml) + slot0 * 256 + row_in_unit;
+        float2 ml[ATT_MAX_SPLIT];
         float m = -INFINITY;
-        for (int pp = 0; pp < nparts; ++pp) m = fmaxf(m, __ldcg(sc.ws_ml + (row0 + static_cast<size_t>(pp) * 256) * 2));
+#pragma unroll
+        for (int pp = 0; pp < ATT_MAX_SPLIT; ++pp) {
+          if (pp < nparts) {
+            ml[pp] = __ldcg(mlp + pp * 256);
+            m = fmaxf(m, ml[pp].x);
+          }
+        }
         l = 0.f;
 #pragma unroll
         for (int c = 0; c < ATT_D; ++c) o[c] = 0.f;
+#pragma unroll 1
         for (int pp = 0; pp < nparts; ++pp) {  // fixed order: the result does not depend on which CTA came last
-          const size_t r = row0 + static_cast<size_t>(pp) * 256;
-          const float2 ml = __ldcg(reinterpret_cast<const float2*>(sc.ws_ml + r * 2));
-          const float w = ex2_approx(ml.x - m);
-          l = fmaf(w, ml.y, l);
-          const float4* src = reinterpret_cast<const float4*>(sc.ws_o + r * ATT_D);
+          float w = 0.f;
+#pragma unroll
+          for (int k = 0; k < ATT_MAX_SPLIT; ++k)
+            if (k == pp) w = ex2_approx(ml[k].x - m) , l = fmaf(w, ml[k].y, l);
+          const float4* src = reinterpret_cast<const float4*>(sc.ws_o) + (slot0 + pp) * (16 * 256) + row_in_unit;
+          float4 f[ATT_D / 4];
+#pragma unroll
+          for (int c = 0; c < ATT_D / 4; ++c) f[c] = __ldcg(src + c * 256);
 #pragma unroll
           for (int c = 0; c < ATT_D / 4; ++c) {
-            const float4 f = __ldcg(src + c);
-            o[4 * c] = fmaf(w, f.x, o[4 * c]);
-            o[4 * c + 1] = fmaf(w, f.y, o[4 * c + 1]);
-            o[4 * c + 2] = fmaf(w, f.z, o[4 * c + 2]);
-            o[4 * c + 3] = fmaf(w, f.w, o[4 * c + 3]);
+            o[4 * c] = fmaf(w, f[c].x, o[4 * c]);
+            o[4 * c + 1] = fmaf(w, f[c].y, o[4 * c + 1]);
+            o[4 * c + 2] = fmaf(w, f[c].z, o[4 * c + 2]);
+            o[4 * c + 3] = fmaf(w, f[c].w, o[4 * c + 3]);
           }
         }
       }
     }
+    if (tracer2) trace[1028] = clock64();
     const int row = q_pair * 256 + row_in_unit;
     if (store && row < p.Sq) {
       const float inv_l = 1.f / l;
@@ -721,7 +745,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 
 namespace {
 // workspace layout of the split units of one launch (at most one wave of them): partial O | (m, l) | tickets
-constexpr int64_t kWsSlots = 160;  // >= SM count
+constexpr int64_t kWsSlots = 640;  // parts of all split units of one launch (<= 4 waves of short CTAs)
 constexpr int64_t kWsOBytes = kWsSlots * 256 * mvd::ATT_D * 4;
 constexpr int64_t kWsMlBytes = kWsSlots * 256 * 2 * 4;
 constexpr int64_t kWsCntBytes = kWsSlots * 4;
@@ -783,7 +807,8 @@ extern "C" int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch
   // sites still spread over the SMs
   const long q_pairs = (s_q + 255) / 256;
   const long units = q_pairs * heads * batch;
-  const bool two_tiles = (s_q >= 512) && units >= (workspace ? static_cast<long>(sms) : 2L * sms);
+  // with a workspace even a launch of fewer units than SMs fills the machine (every unit is split along S_kv)
+  const bool two_tiles = (s_q >= 512) && units >= (workspace ? static_cast<long>(sms) / 4 : 2L * sms);
   if (two_tiles) {
     MVD_CHECK(units < (1L << 30), "attention: too many tiles");
     PairSched sc;
@@ -803,12 +828,26 @@ extern "C" int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch
       return e == nullptr || e[0] != '0';
     }();
     if (workspace && split_on && rem > 0) {
-      int split = sms / rem;  // the parts of the tail units fill one more wave of short CTAs
-      if (split > n_blocks / 4) split = n_blocks / 4;
-      if (split > ATT_MAX_SPLIT) split = ATT_MAX_SPLIT;
-      if (split >= 2 && static_cast<int64_t>(rem) * split <= kWsSlots) {
-        sc.n_full = static_cast<int>(units) - rem;
-        sc.split = split;
+      // `tail` units share the last wave. Split them into s parts each so that the wave is made of short CTAs:
+      // cost model in KV blocks, with kFixed blocks of fixed cost per CTA (prologue, partial write, merge):
+      //   waves(s) * (n_blocks / s + kFixed),  waves(s) = ceil(tail * s / SMs)   (one wave when the tail is < 1 wave of units)
+      // This also covers launches with fewer units than SMs (view-sharded ranks, B = 1 or 2): tail = all units.
+      const int tail = rem;
+      int best = 1;
+      constexpr double kFixed = 4.0;  // prologue + partial write + merge of one CTA, in KV blocks (measured ~8 us)
+      double best_cost = (static_cast<double>((tail + sms - 1) / sms)) * (n_blocks + kFixed);
+      for (int sp = 2; sp <= ATT_MAX_SPLIT; ++sp) {
+        if (n_blocks / sp < 2 || static_cast<int64_t>(tail) * sp > kWsSlots) break;
+        const double waves = static_cast<double>((static_cast<int64_t>(tail) * sp + sms - 1) / sms);
+        const double cost = waves * (static_cast<double>(n_blocks) / sp + kFixed);
+        if (cost < best_cost * 0.9) {
+          best_cost = cost;
+          best = sp;
+        }
+      }
+      if (best >= 2) {
+        sc.n_full = static_cast<int>(units) - tail;
+        sc.split = best;
         char* w = static_cast<char*>(workspace);
         sc.ws_o = reinterpret_cast<float*>(w);
         sc.ws_ml = reinterpret_cast<float*>(w + kWsOBytes);

@@ -33,10 +33,15 @@ def run(B, H, S, reps=20):
     err = (out.float() - ref).abs().max().item()
     print(f"  B={B} h={H} S={S}: {ms * 1e3:7.1f} us  {4.0 * S * S * C * B / ms / 1e9:6.0f} TFLOP/s  max|err| {err:.2e}", flush=True)
 if os.environ.get("TRACE") == "1":
-    buf = torch.zeros(2 * 8 * 64, dtype=torch.int64, device="cuda")
+    buf = torch.zeros(2048, dtype=torch.int64, device="cuda")
     os.environ["MVD_ATTN_TRACE_PTR"] = str(buf.data_ptr())
-    run(8, 5, 4096, reps=1)
-    t = buf.cpu().reshape(2, 64, 8)
+    for B in (2, 8):
+        buf.zero_()
+        run(B, 5, 4096, reps=1)
+        c = buf.cpu()[1024:1032].tolist()
+        print(f"  last CTA of the grid at B={B}: {c[6]} KV blocks, {c[7]} parts; cycles: main loop {c[1] - c[0]}, wait O {c[2] - c[1]}, "
+              f"partial write + fence {c[3] - c[2]}, ticket + merge {c[4] - c[3]}")
+    t = buf.cpu()[:1024].reshape(2, 64, 8)
     names = ["S ready", "S in regs (+PV(j-1) done)", "row max", "O rescale", "exp + P stored", "P published"]
     for wg in (0, 1):
         rows = t[wg, 8:24, :7] - t[0, 0, 0]
