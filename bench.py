@@ -289,7 +289,21 @@ def build_rank_session(dev, sp, pipe, use_graph, guidance=GUIDANCE):
     _, s2, inp, noises = build_session(dev, sp["views_local"], sp["view0"], sp["cfg_local"], sp["cfg_branch"],
                                        use_graph=use_graph, pipe=pipe, sharded=sp["world"] > 1)
     if sp["cfg_local"] == 1 and CFG == 2:
-        mdist.install_cfg_pair_exchange(s2, sp, guidance)
+        if sp.get("emulated"):  # no partner rank: the pair's other prediction is a copy of ours (same kernels, no NCCL)
+            from mvd_b200 import ops
+            gathered = torch.empty((CFG,) + tuple(s2.latents.shape), device=dev, dtype=torch.float32)
+
+            def step(sess=s2):
+                out = sess.forward_unet(sess.latents)
+                gathered[0].copy_(out)
+                gathered[1].copy_(out)
+                ops.cfg_ddpm_step_table(gathered, sess.latents, sess.noise_table, CFG, guidance, sess.coef, sess.step_idx)
+                sess.advance()
+
+            s2._eager_step = step
+            s2.guidance = guidance
+        else:
+            mdist.install_cfg_pair_exchange(s2, sp, guidance)
     return s2, inp, noises
 
 
@@ -324,6 +338,11 @@ def run_ours(args):
     # Headline = ONE object (BASELINE.json configs[1] at N = 1, configs[2] at N > 1): its V x cfg samples are split over
     # the ranks (strong scaling). Every rank holds the full model; reference features cover all views on every rank.
     sp = mdist.shard_plan(VIEWS, CFG, world, rank)
+    if args.shard_of > 1:  # single-GPU stand-in for rank 0 of an N-rank job (profiling the per-rank step)
+        if world != 1:
+            raise SystemExit("--shard-of emulates one rank on ONE GPU")
+        sp = mdist.shard_plan(VIEWS, CFG, args.shard_of, 0)
+        sp["emulated"] = True
     pipe = build_pipeline(dev)
     if args.profile:  # one eager step between cudaProfilerStart/Stop (ncu --profile-from-start off)
         sess, inp, noises = build_rank_session(dev, sp, pipe, use_graph=False)
@@ -459,7 +478,9 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             result["line"]["sample_parallel"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
-    if world == 1 and rank == 0:
+    if args.shard_of > 1:
+        result["line"]["emulated_rank_of"] = args.shard_of
+    if world == 1 and rank == 0 and args.shard_of == 1:
         result["line"]["roofline"] = attention_roofline(dev, pk, how)
         if not args.no_parity:
             try:
@@ -516,6 +537,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard-of", type=int, default=1, help="single GPU: run rank 0's share of an N-rank view-sharded job "
+                    "(no NCCL; for profiling the per-rank step)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed model (N = 1)")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the sample-parallel (replica) side figure")
     ap.add_argument("--profile", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")

@@ -65,6 +65,10 @@ struct GemmArgs {
   const float* film_scale;
   const float* film_shift;
   int film_ld;
+  // split-K (SPLIT kernels): tiles_total counts (tile, k-slice) work items, slice fastest
+  int splits;                // k-slices per output tile
+  float4* ws_partial;        // [tile][slice][BN/4][128 rows] fp32 partial accumulators (lane = row: coalesced)
+  unsigned int* ws_tickets;  // [tile][4] arrival counters, one per 32-row warp slab; zero between launches
 };
 
 constexpr int WS_MAX_KBLOCKS = 5;  // weight-stationary tiles: K <= 320
@@ -104,16 +108,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return x * (x >= 0.f ? 1.0f - half_erfc : half_erfc);
 }
 
-// Round 2 measured and removed two variants of this kernel (profiles/r2_gemm_variants.txt): CTA-pair tiles
-// (cta_group::2, 256 x BN; 5-20 % slower at every M = 32768 linear, step 13.74 vs 13.26 ms) and split-K for the
-// under-filled 8x8 level (the fp32 fix-up traffic cost more than the idle SMs: 30.6 vs 13.8 us at N=1280, K=2560).
-template <int BN, bool S2, bool WS = false>
+// Round 2 measured and removed CTA-pair tiles (cta_group::2, 256 x BN; 5-20 % slower at every M = 32768 linear, step
+// 13.74 vs 13.26 ms; profiles/r2_gemm_variants.txt).
+// SPLIT: split-K for launches that fill a fraction of the machine with LONG k-loops — the 16x16 and 8x8 levels of a
+// view-sharded rank (1-2 samples: 20-40 tiles, 180-360 k-blocks each, 25-39 us on 20-40 SMs). Each work item is a
+// (tile, k-slice); every CTA writes its fp32 partial tile to a workspace (column-chunk major, so a warp's 32 rows are
+// contiguous), and per 32-row slab the LAST arriving warp (ticket counter, re-armed for the next launch) adds the
+// slices in slice order — deterministic — and runs the normal epilogue on the sum. Round 1's version of this (row-
+// major partials, used at M = 512 where the k-loops are short) measured slower and is what round 2 removed.
+template <int BN, bool S2, bool WS = false, bool SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
                  const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapOut,
                  const __grid_constant__ CUtensorMap mapRes, const GemmArgs p) {
   using L = SmemLayout<BN, WS>;
-  static_assert(!WS || !S2, "weight-stationary tiles: 1-tap only");
+  static_assert(!WS || (!S2 && !SPLIT), "weight-stationary tiles: 1-tap only, un-split");
   const int unit = blockIdx.x;
   const int n_units = gridDim.x;
   extern __shared__ uint8_t smem_raw[];
@@ -173,16 +182,21 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
           tma_load_2d(b_res + kb * L::B_BYTES, &mapB, b_full, kb * BK, n_tile_fixed * BN);
       }
       for (int t = unit; t < p.tiles_total; t += n_units) {
-        const int n_tile = t % p.tiles_n;
-        int m_tile = t / p.tiles_n;
+        const int tile = SPLIT ? t / p.splits : t;
+        const int ks = SPLIT ? t - tile * p.splits : 0;
+        const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
+        const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
+        const int n_tile = tile % p.tiles_n;
+        int m_tile = tile / p.tiles_n;
         const int x0 = (m_tile % p.tiles_x) * p.TW;
         m_tile /= p.tiles_x;
         const int y0 = (m_tile % p.tiles_y) * p.TH;
         const int n0 = (m_tile / p.tiles_y) * p.TN;
-        for (int tap = 0; tap < p.ntaps; ++tap) {
+        int tap = kb0 / p.kc_per_tap, kc = kb0 - tap * p.kc_per_tap;
+        for (int kb = kb0; kb < kb1; ++kb) {
           const int ky = (p.ntaps == 9) ? tap / 3 : 1;
           const int kx = (p.ntaps == 9) ? tap % 3 : 1;
-          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+          {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + stage * L::STAGE_BYTES;
             uint8_t* sb = sa + L::A_BYTES;
@@ -209,6 +223,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
               phase ^= 1;
             }
           }
+          if (++kc == p.kc_per_tap) {
+            kc = 0;
+            ++tap;
+          }
         }
       }
     }
@@ -232,7 +250,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tb + acc * L::ACC_STRIDE;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      const int ks = SPLIT ? t % p.splits : 0;
+      const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
+      const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
@@ -241,7 +262,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
                                   : umma_desc_sw128(sa + L::A_BYTES);
         if (elect_one()) {
           // +32 B per K=16 step inside the 128-B swizzle row (start-address field is addr >> 4)
-          umma_ss(d_tmem, adesc, bdesc, idesc, kb != 0);
+          umma_ss(d_tmem, adesc, bdesc, idesc, kb != kb0);
 #pragma unroll
           for (int k = 1; k < BK / 16; ++k) umma_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, 1);
           umma_commit(&empty[stage]);
@@ -277,8 +298,9 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     uint32_t g = 0;  // running chunk counter -> staging buffer + barrier parity
     int it = wg;     // index of the tile in this CTA's sequence: stage it & 1 == wg
     for (int t = unit + wg * n_units; t < p.tiles_total; t += 2 * n_units, it += 2) {
-      const int n_tile = t % p.tiles_n;
-      int m_tile = t / p.tiles_n;
+      const int tile = SPLIT ? t / p.splits : t;
+      const int n_tile = tile % p.tiles_n;
+      int m_tile = tile / p.tiles_n;
       const int x0 = (m_tile % p.tiles_x) * p.TW;
       m_tile /= p.tiles_x;
       const int y0 = (m_tile % p.tiles_y) * p.TH;
@@ -287,6 +309,40 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const int col_base = n_tile * out_cols_per_tile;
+
+      [[maybe_unused]] const float4* part_rd = nullptr;
+      if constexpr (SPLIT) {
+        // publish this k-slice's fp32 partial tile, hand the accumulator back, take a ticket for the 32-row slab
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+        const uint32_t t_part = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
+        const int ks = t - tile * p.splits;
+        float4* part = p.ws_partial + (static_cast<size_t>(tile) * p.splits + ks) * (BN / 4 * BM) + row;
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(t_part + c * 32, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            part[static_cast<size_t>(c * 8 + j) * BM] =
+                make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                            __uint_as_float(r[4 * j + 3]));
+        }
+        tc_fence_before();
+        __threadfence();  // partial rows visible device-wide before the ticket is taken
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          mbar_arrive(&tmem_empty[acc]);
+          unsigned int* tk = p.ws_tickets + tile * 4 + q;
+          last = atomicAdd(tk, 1u) == static_cast<unsigned int>(p.splits - 1);
+          if (last) *tk = 0u;  // re-arm for the next launch
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        __threadfence();
+        part_rd = p.ws_partial + static_cast<size_t>(tile) * p.splits * (BN / 4 * BM) + row;
+      }
 
       // prefetch residual slabs for the first two chunks (their buffers are free: at most one store
       // group from the previous tile may still be reading, and it is neither of these two buffers
@@ -303,8 +359,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
       }
 
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tc_fence_after();
+      if constexpr (!SPLIT) {
+        mbar_wait(&tmem_full[acc], acc_phase);
+        tc_fence_after();
+      }
       const uint32_t t_acc = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
       int img = ln + n0 + (x0 + lx) / p.rows_per_img;
       img = img < p.img_max ? img : p.img_max;
@@ -348,7 +406,19 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         float v[32];
         if (!p.geglu) {
-          {
+          if constexpr (SPLIT) {
+            // slices in slice order (fixed summation order whichever CTA arrived last); L2-coherent, coalesced loads
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            for (int sl = 0; sl < p.splits; ++sl) {
+              const float4* src = part_rd + static_cast<size_t>(sl) * (BN / 4 * BM) + static_cast<size_t>(c * 8) * BM;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 f = __ldcg(src + static_cast<size_t>(j) * BM);
+                v[4 * j] += f.x; v[4 * j + 1] += f.y; v[4 * j + 2] += f.z; v[4 * j + 3] += f.w;
+              }
+            }
+          } else {
             uint32_t r[32];
             tmem_ld_32x32b_x32(t_acc + c * 32, r);
             tmem_ld_wait();
@@ -487,10 +557,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       if (p.stats_out != nullptr && ln == 0 && x0 + lx < p.rows_total)
         p.stats_out[static_cast<size_t>(x0 + lx) * p.tiles_n + n_tile] = make_float2(st_sum, st_sq);
-      // accumulator fully read -> hand the TMEM stage back to the MMA warp
+      // accumulator fully read -> hand the TMEM stage back to the MMA warp (SPLIT: already done above)
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (!SPLIT && lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if (lane == 0) tma_store_wait_all0();
   }
@@ -606,10 +676,32 @@ static int pick_bn(int N, int M_tiles, bool geglu) {
 struct GemmPlan {
   int TW, TH, TN, tiles_m;
   int bn;
-  bool ws;  // weight-stationary 128-wide tiles (grid must then be a multiple of the column-tile count)
+  bool ws;     // weight-stationary 128-wide tiles (grid must then be a multiple of the column-tile count)
+  int splits;  // k-slices per tile (needs a workspace)
 };
+
+constexpr int64_t SPLITK_TICKET_BYTES = 4096 * sizeof(unsigned int);
+constexpr int SPLITK_BN = 64;
+// Split-K pays when few tiles run long k-loops: a CTA moves one k-block per ~0.1 us whatever the tile width, and the
+// fix-up (fp32 partial tile out, splits tiles back in through L2, ticket) costs about as much as 16 + 4 * splits of them.
+static int pick_splits(int tiles, int k_blocks, int64_t ws_bytes) {
+  const int sms = sm_count();
+  if (ws_bytes <= SPLITK_TICKET_BYTES || tiles * 2 > sms || tiles > 1024) return 1;
+  int best = 1;
+  double best_cost = k_blocks;
+  for (int sp = 2; sp <= 8; ++sp) {
+    if (tiles * sp > sms || k_blocks / sp < 16) break;
+    if (SPLITK_TICKET_BYTES + static_cast<int64_t>(tiles) * sp * BM * SPLITK_BN * 4 > ws_bytes) break;
+    const double cost = static_cast<double>((k_blocks + sp - 1) / sp) + 16.0 + 4.0 * sp;
+    if (cost < best_cost * 0.8) {
+      best_cost = cost;
+      best = sp;
+    }
+  }
+  return best;
+}
 static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, int stride, int geglu, int force_bn,
-                          bool two_source) {
+                          bool two_source, int64_t ws_bytes = 0) {
   GemmPlan pl;
   pick_tile(Nimg, H, W, &pl.TW, &pl.TH, &pl.TN);
   pl.tiles_m = ((W + pl.TW - 1) / pl.TW) * ((H + pl.TH - 1) / pl.TH) * ((Nimg + pl.TN - 1) / pl.TN);
@@ -620,6 +712,15 @@ static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, 
           (force_bn == 0 || force_bn == 128) && (!geglu || force_bn == 128) && !two_source &&
           Cout / 128 <= sm_count() && pl.tiles_m * (Cout / 128) >= 4 * sm_count();
   if (pl.ws) pl.bn = 128;
+  pl.splits = 1;
+  if (!pl.ws && !geglu && stride == 1 && (force_bn == 0 || force_bn == SPLITK_BN)) {
+    const int tiles64 = ((Cout + SPLITK_BN - 1) / SPLITK_BN) * pl.tiles_m;
+    const int sp = pick_splits(tiles64, ntaps * (Cin / 64), ws_bytes);
+    if (sp > 1) {
+      pl.splits = sp;
+      pl.bn = SPLITK_BN;
+    }
+  }
   return pl;
 }
 
@@ -653,7 +754,9 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
 
   GemmArgs g;
   memset(&g, 0, sizeof(g));
-  const GemmPlan pl = plan_gemm(Nimg, H, W, Cin, Cout, ntaps, stride, geglu, force_bn, a2 != nullptr);
+  const bool plain_ex = ex == nullptr || (ex->ln_stats == nullptr && ex->stats_out == nullptr);
+  const GemmPlan pl = plan_gemm(Nimg, H, W, Cin, Cout, ntaps, stride, geglu, force_bn, a2 != nullptr,
+                                (ex != nullptr && ex->workspace != nullptr && plain_ex) ? ex->workspace_bytes : 0);
   const int TW = pl.TW, TH = pl.TH, TN = pl.TN;
   g.TW = TW; g.TH = TH; g.TN = TN;
   g.tiles_x = (W + TW - 1) / TW;
@@ -681,6 +784,13 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   g.tiles_n = (Cout + BN - 1) / BN;
   g.tiles_total = g.tiles_n * tiles_m;
   g.rows_total = W;
+  g.splits = pl.splits;
+  if (pl.splits > 1) {
+    MVD_CHECK((reinterpret_cast<uintptr_t>(ex->workspace) & 15) == 0, "gemm: workspace must be 16-byte aligned");
+    g.ws_tickets = static_cast<unsigned int*>(ex->workspace);
+    g.ws_partial = reinterpret_cast<float4*>(static_cast<char*>(ex->workspace) + SPLITK_TICKET_BYTES);
+    g.tiles_total *= pl.splits;  // work items: (tile, k-slice), slice fastest
+  }
   if (ex != nullptr) {
     const bool linear_mode = ntaps == 1 && H == 1 && Nimg == 1;
     if (ex->ln_stats != nullptr) {
@@ -775,6 +885,17 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   }
 
   if (pl.ws) return launch_ws(mA, mA2, mB, mO, mR, g, stream);
+  if (pl.splits > 1) {
+    using L = SmemLayout<SPLITK_BN>;
+    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<SPLITK_BN, false, false, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    const int grid = g.tiles_total < sm_count() ? g.tiles_total : sm_count();
+    MVD_CUDA(launch_pdl(gemm_conv_kernel<SPLITK_BN, false, false, true>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL,
+                        stream, mA, mA2, mB, mO, mR, g));
+    MVD_CUDA(cudaGetLastError());
+    count_launches(1);
+    return MVD_OK;
+  }
 #define MVD_LAUNCH_BN(bn)                                                               \
   case bn:                                                                              \
     return stride == 2 ? launch_one<bn, true>(mA, mA2, mB, mO, mR, g, stream)           \

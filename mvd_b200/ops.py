@@ -39,10 +39,15 @@ def _rows2d(t: torch.Tensor, name: str):
     return t.data_ptr(), t.stride(0), t.shape[0], t.shape[1]
 
 
+# split-K of under-filled GEMM / conv launches (csrc/gemm.cu); MVD_SPLIT_K=0 switches it off for A/B runs
+SPLIT_K = os.environ.get("MVD_SPLIT_K", "1") != "0"
+
+
 class _GemmExtras(ctypes.Structure):  # mirrors mvd_gemm_extras (include/mvd_b200.h)
     _fields_ = [("ln_stats", ctypes.c_void_p), ("ln_colsum", ctypes.c_void_p), ("ln_parts", ctypes.c_int),
                 ("ln_eps", ctypes.c_float), ("stats_out", ctypes.c_void_p), ("stats_parts", ctypes.c_int),
-                ("film_scale", ctypes.c_void_p), ("film_shift", ctypes.c_void_p), ("film_ld", ctypes.c_int)]
+                ("film_scale", ctypes.c_void_p), ("film_shift", ctypes.c_void_p), ("film_ld", ctypes.c_int),
+                ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_int64)]
 
 
 class RowStats:
@@ -81,11 +86,15 @@ def linear_column_tiles(M: int, N: int, K: int, geglu: bool = False, tile_n: int
     return got
 
 
-def _extras(ln: Optional["LNFold"], stats: Optional["RowStats"], film, N: int, M: int):
-    if ln is None and stats is None and film is None:
-        return None, ()
+_GEMM_WS_FLOATS = 4 << 20  # 16 MiB of split-K scratch per (device, stream)
+
+
+def _extras(ln: Optional["LNFold"], stats: Optional["RowStats"], film, N: int, M: int, device=None):
     ex = _GemmExtras()
     keep = []
+    if device is not None and SPLIT_K:
+        ws = _workspace(device, _GEMM_WS_FLOATS, "gemm")
+        ex.workspace, ex.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     if ln is not None:
         _contig(ln.stats.buf, "ln.stats", F32)
         _contig(ln.colsum, "ln.colsum", F32)
@@ -166,10 +175,10 @@ def linear(
         stats = RowStats(torch.empty((M, parts, 2), device=a.device, dtype=F32), parts, n_out)
     if film is not None and rows_per_group <= 0:
         raise ValueError("film needs rows_per_group > 0")
-    ex, _keep = _extras(ln, stats, film, N, M)
+    ex, _keep = _extras(ln, stats, film, N, M, a.device)
     check(
         lib().mvd_linear_ex_bf16(pa, lda, k1, pa2, lda2, k2, pw, ldw, _p(bias), pg, ldg, rows_per_group, pr, ldr, po,
-                                 ldo, M, N, int(geglu), tile_n, None if ex is None else ctypes.byref(ex), _stream()),
+                                 ldo, M, N, int(geglu), tile_n, ctypes.byref(ex), _stream()),
         "mvd_linear_ex_bf16",
     )
     return (out, stats) if want_stats else out
@@ -221,15 +230,13 @@ def conv3x3(
         _req(img_bias, "img_bias", torch.float32)
         if tuple(img_bias.shape) != (n, cout) or img_bias.stride(1) != 1:
             raise ValueError("img_bias must be fp32 [N, Cout] with unit inner stride")
-    ex = None
-    if film is not None:  # camera FiLM of a block output, per image
-        if film[0].shape[0] != n:
-            raise ValueError("film rows must match the image count")
-        ex, _keep = _extras(None, None, film, cout, n)
+    if film is not None and film[0].shape[0] != n:  # camera FiLM of a block output, per image
+        raise ValueError("film rows must match the image count")
+    ex, _keep = _extras(None, None, film, cout, n, x.device)
     check(
         lib().mvd_conv3x3_ex_bf16(_p(x), c1, _p(x2), c2, _p(w), _p(bias), _p(img_bias),
                                   0 if img_bias is None else img_bias.stride(0), _p(residual), _p(out), n, ho, wo,
-                                  cout, stride, tile_n, None if ex is None else ctypes.byref(ex), _stream()),
+                                  cout, stride, tile_n, ctypes.byref(ex), _stream()),
         "mvd_conv3x3_ex_bf16",
     )
     return out

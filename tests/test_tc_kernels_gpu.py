@@ -102,8 +102,9 @@ def test_linear_row_stats_and_layernorm_fold(M, C, N):
     xs = x.float()
     got = st.buf.sum(1)
     assert st.buf.shape == (M, st.parts, 2)
-    assert torch.allclose(got[:, 0], xs.sum(1), rtol=1e-4, atol=1e-2)
-    assert torch.allclose(got[:, 1], (xs * xs).sum(1), rtol=1e-4, atol=1e-2)
+    # the statistics are taken on the fp32 values before their bf16 rounding (zero-mean noise, 2^-9 relative per element)
+    assert torch.allclose(got[:, 0], xs.sum(1), rtol=0, atol=0.02 * C ** 0.5)
+    assert torch.allclose(got[:, 1], (xs * xs).sum(1), rtol=3e-3, atol=0)
 
     norm = torch.nn.LayerNorm(C).cuda()
     with torch.no_grad():
@@ -134,6 +135,35 @@ def test_linear_row_stats_and_layernorm_fold(M, C, N):
     out_g = ops.linear(x, wg, bias=cst.view(-1).to(torch.bfloat16), geglu=True, tile_n=256,
                        ln=ops.LNFold(st, colsum, norm.eps))
     _cmp(out_g, ref_g, f"layernorm fold + geglu {M}x{C}", atol=8e-2)
+
+
+@pytest.mark.parametrize("n,hw,cin,cin2,cout", [(1, 8, 1280, 0, 1280), (1, 8, 1280, 1280, 1280), (2, 8, 1280, 1280, 1280),
+                                                (1, 16, 1280, 640, 1280), (1, 16, 640, 0, 1280)])
+def test_conv3x3_split_k(n, hw, cin, cin2, cout):
+    """Few tiles, long k-loops (the 8x8 / 16x16 levels of a view-sharded rank): the launch is split along K, the fp32
+    partial tiles are summed in slice order by the last-arriving CTA. Same result as the fp32 reference, bit-identical
+    across launches, ticket counters re-armed; the planner reports the un-split plan without a workspace."""
+    from mvd_b200 import ops
+
+    x = _randn(n, hw, hw, cin, seed=1)
+    x2 = _randn(n, hw, hw, cin2, seed=5) if cin2 else None
+    w9 = _randn(cout, 9 * (cin + cin2), scale=(9 * (cin + cin2)) ** -0.5, seed=2)
+    b = _randn(cout, seed=3)
+    ib = torch.randn(n, cout, device="cuda")
+    r = _randn(n, hw, hw, cout, seed=4)
+    outs = [ops.conv3x3(x, w9, bias=b, img_bias=ib, residual=r, x2=x2).clone() for _ in range(3)]
+    torch.cuda.synchronize()
+    _cmp(outs[0], _conv_ref(x, w9, b, ib, r, 1, x2=x2), f"conv split-K {n}x{hw}x{hw} {cin}+{cin2}->{cout}", atol=4e-2)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_linear_split_k_long_k():
+    from mvd_b200 import ops
+
+    M, K, N = 64, 5120, 1280  # ff.net[2] at the 8x8 level of one sample
+    a, w, b, r = _randn(M, K, seed=1), _randn(N, K, scale=K ** -0.5, seed=2), _randn(N, seed=3), _randn(M, N, seed=4)
+    out = ops.linear(a, w, bias=b, residual=r)
+    _cmp(out, a.float() @ w.float().t() + b.float() + r.float(), "linear split-K 64x5120x1280", atol=3e-2)
 
 
 def test_film_epilogue_linear_and_conv():
