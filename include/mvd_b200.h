@@ -32,6 +32,11 @@ const char* mvd_last_error(void);
 int mvd_abi_version(void);
 /* Number of CUDA kernels this library has launched (or recorded into a stream capture) in this process. */
 int64_t mvd_kernel_launch_count(void);
+/* Process-wide switch for programmatic dependent launch of every kernel of this library (the next kernel's prologue —
+ * barrier init, TMEM allocation, descriptor prefetch — overlaps the previous kernel's tail; data dependences are kept by
+ * griddepcontrol.wait). Pays for launch-bound steps (1-2 samples per GPU), costs ~3 % for throughput-bound ones; the
+ * environment variable MVD_PDL=0/1 overrides it. No reference analogue (scheduling detail). */
+int mvd_set_launch_overlap(int on);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Tensor-core contractions (tcgen05 + TMEM + TMA), csrc/gemm.cu

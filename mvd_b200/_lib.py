@@ -49,6 +49,7 @@ _SIGNATURES = {
     "mvd_last_error": (c_char_p, []),
     "mvd_abi_version": (_I, []),
     "mvd_kernel_launch_count": (_L, []),
+    "mvd_set_launch_overlap": (_I, [_I]),
     "mvd_linear_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P]),
     "mvd_conv3x3_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P]),
     "mvd_linear_ex_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P, _P]),

@@ -36,6 +36,17 @@ OVERLAP_BRANCHES = os.environ.get("MVD_OVERLAP_BRANCHES", "1") != "0"
 _branch_streams: Dict[int, "torch.cuda.Stream"] = {}
 
 
+_sm_counts: Dict[int, int] = {}
+
+
+def _sm_count(device: torch.device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    n = _sm_counts.get(idx)
+    if n is None:
+        n = _sm_counts[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return n
+
+
 def _branch_stream(device: torch.device) -> "torch.cuda.Stream":
     idx = device.index if device.index is not None else torch.cuda.current_device()
     s = _branch_streams.get(idx)
@@ -217,14 +228,24 @@ class ImageCrossAttentionProcessor(nn.Module):
                 side = _branch_stream(hidden_states.device)
                 fork, join = torch.cuda.Event(), torch.cuda.Event()
                 fork.record(main)
-                # the side launch goes first and finishes first: it never owns the machine's last wave, so only the
-                # main launch splits a tail, and only its share of the COMBINED last wave (co_units)
+                # Who splits its last partial wave along S_kv (ops.attention): a launch of >= 1 wave of units shares
+                # the machine's last wave with its sibling — the side launch goes first and finishes first, so only
+                # the main one splits, and only its share of the COMBINED last wave (co_units). Small launches (a
+                # view-sharded rank: fewer units than SMs) both split. Next to the tiny text attention the reference
+                # branch simply owns the machine.
+                units = ops.attention_units(b, self.heads, s)
+                big = units >= _sm_count(hidden_states.device)
+                if pk["is_cross"]:
+                    side_kw, main_kw = dict(split_tail=True), dict(split_tail=False)
+                elif big:
+                    side_kw, main_kw = dict(split_tail=False), dict(co_units=units)
+                else:
+                    side_kw, main_kw = dict(co_units=units), dict(co_units=units)
                 with torch.cuda.stream(side):
                     side.wait_event(fork)
-                    ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:], split_tail=False)
+                    ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:], **side_kw)
                     join.record(side)
-                ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c],
-                              co_units=ops.attention_units(b, self.heads, s))
+                ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c], **main_kw)
                 main.wait_event(join)
             else:
                 ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])

@@ -139,7 +139,19 @@ class CameraEncoder(nn.Module):
         return emb
 
     def forward(self, camera_data: Dict[str, torch.Tensor]) -> torch.Tensor:
-        raise NotImplementedError("call encode_cameras(source_camera, target_camera)")
+        """reference camera_encoder.py:173-196: embedding of an already RELATIVE pose {"R": [V,3,3], "T": [V,3]}.
+        Runs the same kernels as encode_cameras through an identity source pose (R_rel = R I^T = R,
+        T_rel = T - R 0 = T)."""
+        R, T = camera_data["R"], camera_data["T"]
+        dev = self.output_norm.weight.device
+        R = R.to(device=dev, dtype=torch.float32).reshape(-1, 3, 3)
+        T = T.to(device=dev, dtype=torch.float32).reshape(-1, 3)
+        if R.shape[0] != T.shape[0]:
+            raise ValueError("camera_data['R'] and ['T'] must hold the same number of poses")
+        target = torch.cat([R, T[:, :, None]], dim=2).contiguous()
+        source = torch.zeros_like(target)
+        source[:, 0, 0] = source[:, 1, 1] = source[:, 2, 2] = 1.0
+        return self.encode_cameras(source, target)
 
     # ---- FiLM ---------------------------------------------------------------------------------------------
     def modulation(self, modulator_name: str, camera_embedding: torch.Tensor) -> torch.Tensor:

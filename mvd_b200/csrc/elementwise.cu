@@ -493,14 +493,11 @@ int mvd_small_linear_f32(const float* x, int64_t ldx, const void* w, const void*
   MVD_CHECK((K & 7) != 0 || ((reinterpret_cast<uintptr_t>(w) & 15) == 0), "small_linear: w must be 16-byte aligned");
   const int kt = K < SL_KTILE ? K : SL_KTILE;
   const size_t smem = static_cast<size_t>(M) * kt * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    MVD_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  SL_MAX_M * SL_KTILE * static_cast<int>(sizeof(float))));
-    MVD_CUDA(cudaFuncSetAttribute(small_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  SL_MAX_M * SL_KTILE * static_cast<int>(sizeof(float))));
-    configured = true;
-  }
+  // per call: cheap, and correct for every device a process may touch
+  MVD_CUDA(cudaFuncSetAttribute(small_linear_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SL_MAX_M * SL_KTILE * static_cast<int>(sizeof(float))));
+  MVD_CUDA(cudaFuncSetAttribute(small_linear_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                SL_MAX_M * SL_KTILE * static_cast<int>(sizeof(float))));
   const int blocks = (N + 8 * SL_RPW - 1) / (8 * SL_RPW);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   auto ww = static_cast<const __nv_bfloat16*>(w);
@@ -546,11 +543,8 @@ int mvd_conv_in_f32_bf16(const float* latents, int n_latents, const float* mod, 
   MVD_CHECK(n_img > 0 && n_latents > 0 && h > 0 && wdt > 0 && c_out % 8 == 0 && c_out <= 1024,
             "conv_in: bad shape Cout=%d", c_out);
   const size_t smem = static_cast<size_t>(c_out) * 37 * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    MVD_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    configured = true;
-  }
+  // per call: cheap, and correct for every device a process may touch
+  MVD_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   MVD_CUDA(launch_pdl(conv_in_kernel, dim3((wdt + 31) / 32, (h + CIN_ROWS - 1) / CIN_ROWS, n_img), dim3(256), smem,
                       static_cast<cudaStream_t>(stream), latents, n_latents, mod, n_cam > 0 ? n_cam : 1, strength,
                       static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(bias),
@@ -565,11 +559,8 @@ int mvd_conv_out_bf16_f32(const void* x, const void* w, const void* bias, float*
   using namespace mvd;
   MVD_CHECK(n_img > 0 && h > 0 && wdt > 0 && c_in % 8 == 0 && c_in <= 1280, "conv_out: bad shape Cin=%d", c_in);
   const size_t smem = static_cast<size_t>(36) * c_in * sizeof(__nv_bfloat16);
-  static bool configured = false;
-  if (!configured) {
-    MVD_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-    configured = true;
-  }
+  // per call: cheap, and correct for every device a process may touch
+  MVD_CUDA(cudaFuncSetAttribute(conv_out_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
   const int64_t pix = static_cast<int64_t>(n_img) * h * wdt;
   MVD_CUDA(launch_pdl(conv_out_kernel, dim3(static_cast<unsigned>((pix + 7) / 8)), dim3(256), smem,
                       static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x),

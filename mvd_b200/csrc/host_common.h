@@ -24,6 +24,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
 // allocation, descriptor prefetch) overlap the predecessor's tail. Opt-in with MVD_PDL=1 (round 1 measured no gain
 // for the graph-replayed step, see host_common.cu).
 bool pdl_enabled();
+void set_pdl(int on);
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                               Args... args) {

@@ -14,6 +14,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cooperative_groups.h>
 #include "host_common.h"
 #include "../../include/mvd_b200.h"
 
@@ -403,6 +404,103 @@ gn_fused_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat1
   }
 }
 
+// Cluster form of gn_fused_kernel for SMALL batches (a view-sharded rank holds 1-2 samples: 32-64 (image, group) slabs
+// for 148 SMs). A cluster of CL CTAs shares one slab by pixel ranges; the two reductions (sum, centred second moment)
+// are completed over distributed shared memory: every CTA publishes its partial in its own shared memory, the
+// cluster synchronises, every CTA adds the CL partials in rank order (deterministic, identical in all CTAs).
+// One launch, CL times the parallelism. (At batch 8 the slabs already fill the machine and this form measured slower.)
+__global__ void __launch_bounds__(GN1_THREADS)
+gn_fused_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2,
+                        int hw, int groups, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
+                        const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
+  extern __shared__ uint32_t gn1_slab[];  // [rows of this CTA][wpp] channel pairs
+  __shared__ float s_red[2][GN1_THREADS / 32];
+  __shared__ float s_part[2];  // this CTA's partial sum / partial centred second moment (read by the whole cluster)
+  const int C = c1 + c2;
+  const int cpg = C / groups;
+  const int wpp = cpg >> 1;
+  const int g = blockIdx.x / CL, n = blockIdx.y;
+  const int rows_per = (hw + CL - 1) / CL;
+  const int r0 = rank * rows_per;
+  const int rows = (r0 + rows_per <= hw) ? rows_per : (hw > r0 ? hw - r0 : 0);
+  const int ppb = blockDim.x / wpp;
+  const int w = threadIdx.x % wpp, p0 = threadIdx.x / wpp;
+  const bool active = p0 < ppb;
+  const int c = g * cpg + 2 * w;
+  GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
+  src.base += static_cast<int64_t>(r0) * src.cs;
+  const int step = ppb * GN1_UNROLL;
+
+  float s = 0.f;
+  for (int p = p0; p < rows; p += step) {
+    uint32_t raw[GN1_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GN1_UNROLL; ++u) {
+      const int pp = p + u * ppb;
+      raw[u] = (active && pp < rows) ? *reinterpret_cast<const uint32_t*>(src.base + static_cast<int64_t>(pp) * src.cs)
+                                     : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < GN1_UNROLL; ++u) {
+      const int pp = p + u * ppb;
+      if (active && pp < rows) {
+        gn1_slab[pp * wpp + w] = raw[u];
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw[u]));
+        s += f.x + f.y;
+      }
+    }
+  }
+  const float cnt = static_cast<float>(hw) * static_cast<float>(cpg);
+  const float s_cta = gn1_block_sum(s, s_red[0]);
+  if (threadIdx.x == 0) s_part[0] = s_cta;
+  cluster.sync();
+  float tot = 0.f;
+  for (int r = 0; r < CL; ++r) tot += *cluster.map_shared_rank(&s_part[0], r);
+  const float mean = tot / cnt;
+
+  float q = 0.f;
+  if (active) {
+    for (int pp = p0; pp < rows; pp += ppb) {
+      const uint32_t r = gn1_slab[pp * wpp + w];
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r));
+      const float d0 = f.x - mean, d1 = f.y - mean;
+      q += d0 * d0 + d1 * d1;
+    }
+  }
+  const float q_cta = gn1_block_sum(q, s_red[1]);
+  if (threadIdx.x == 0) s_part[1] = q_cta;
+  cluster.sync();
+  float qt = 0.f;
+  for (int r = 0; r < CL; ++r) qt += *cluster.map_shared_rank(&s_part[1], r);
+  const float rstd = rsqrtf(qt / cnt + eps);  // biased variance, as torch GroupNorm
+
+  if (active) {
+    const float2 gm = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gamma + c));
+    const float2 bt = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(beta + c));
+    const float a0 = gm.x * rstd, a1 = gm.y * rstd;
+    const float b0 = bt.x - mean * a0, b1 = bt.y - mean * a1;
+    __nv_bfloat16* obase = out + (static_cast<int64_t>(n) * hw + r0) * C + c;
+#pragma unroll 4
+    for (int pp = p0; pp < rows; pp += ppb) {
+      const uint32_t r = gn1_slab[pp * wpp + w];
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r));
+      float y0 = f.x * a0 + b0, y1 = f.y * a1 + b1;
+      if (silu) {
+        y0 = silu_fast(y0);
+        y1 = silu_fast(y1);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(obase + static_cast<int64_t>(pp) * C) = __floats2bfloat162_rn(y0, y1);
+    }
+  }
+  cluster.sync();  // no CTA may exit while a peer can still read its s_part
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers, two-pass (exact mean, then centered variance). Each warp walks
 // rows with a grid stride and loads its next row before it reduces the current one, so a row's memory round trip
@@ -648,11 +746,50 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
     }();
     const int cpg = C / groups;
     const int64_t slab = static_cast<int64_t>(hw) * cpg * 2;
-    if (!two_kernel_only && cpg % 2 == 0 && cpg / 2 <= 128 && slab <= fused_max) {
-      static bool configured = false;
-      if (!configured) {
-        MVD_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN1_MAX_SMEM));
-        configured = true;
+    // small batches: CL CTAs (a thread-block cluster) per slab so that the launch still covers the machine
+    int cl = 1;
+    static const bool cluster_on = [] {
+      const char* e = getenv("MVD_GN_CLUSTER");
+      return e == nullptr || e[0] != '0';
+    }();
+    if (cluster_on && hw >= 256) {
+      const int want = sm_count() / (groups * n_img);
+      cl = want >= 8 ? 8 : want >= 4 ? 4 : want >= 2 ? 2 : 1;
+      while (cl > 1 && hw / cl < 64) cl >>= 1;
+    }
+    const int64_t slab_cta = static_cast<int64_t>((hw + cl - 1) / cl) * cpg * 2;
+    if (!two_kernel_only && cpg % 2 == 0 && cpg / 2 <= 128 && slab_cta <= fused_max) {
+      // per call: cheap, and correct for every device a process may touch
+      MVD_CUDA(cudaFuncSetAttribute(gn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN1_MAX_SMEM));
+      if (cl > 1) {
+        const int rows_per = (hw + cl - 1) / cl;
+        const size_t smem = static_cast<size_t>(rows_per) * cpg * 2;
+        const int64_t words = static_cast<int64_t>(smem) / 4;
+        const int threads1 = words >= 8192 ? GN1_THREADS : (words >= 1024 ? 256 : 128);
+        MVD_CUDA(cudaFuncSetAttribute(gn_fused_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GN1_MAX_SMEM));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(groups * cl, n_img);
+        cfg.blockDim = dim3(threads1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        int na = 1;
+        if (pdl_enabled()) {
+          attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[na].val.programmaticStreamSerializationAllowed = 1;
+          ++na;
+        }
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        MVD_CUDA(cudaLaunchKernelEx(&cfg, gn_fused_cluster_kernel, a1, c1, a2, c2, hw, groups, eps, silu, gm, bt, oo));
+        MVD_CUDA(cudaGetLastError());
+        count_launches(1);
+        return MVD_OK;
       }
       const int64_t words = slab / 4;
       const int threads1 = words >= 8192 ? GN1_THREADS : (words >= 1024 ? 256 : 128);

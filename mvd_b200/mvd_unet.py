@@ -40,10 +40,32 @@ class UNetOutput(NamedTuple):
 
 def _resolve_unet_config(pretrained_model_name_or_path) -> dict:
     """No network and no diffusers here: the UNet is built from the SD2.1 architecture (random init) and weights
-    are loaded afterwards with load_state_dict (keys match diffusers'). A dict overrides config entries."""
+    are loaded afterwards (MultiViewUNet.load_base_weights; keys match diffusers'). A dict overrides config entries."""
     if isinstance(pretrained_model_name_or_path, dict):
         return dict(pretrained_model_name_or_path)
     return {}
+
+
+def _find_unet_weights(path) -> Optional[str]:
+    """A local diffusers checkpoint directory (…/unet/diffusion_pytorch_model.{safetensors,bin}) or a weights file."""
+    if not isinstance(path, (str, os.PathLike)):
+        return None
+    path = os.fspath(path)
+    cands = [path] if os.path.isfile(path) else [
+        os.path.join(path, sub, name) for sub in ("unet", "") for name in
+        ("diffusion_pytorch_model.safetensors", "diffusion_pytorch_model.bin")]
+    for c in cands:
+        if os.path.isfile(c):
+            return c
+    return None
+
+
+def _read_state_dict(file: str) -> Dict[str, torch.Tensor]:
+    if file.endswith(".safetensors"):
+        from safetensors.torch import load_file
+
+        return load_file(file)
+    return torch.load(file, map_location="cpu", weights_only=True)
 
 
 class MultiViewUNet(nn.Module):
@@ -88,6 +110,39 @@ class MultiViewUNet(nn.Module):
         self.fuse_up_film = FUSE_UP_FILM  # camera FiLM of the up blocks applied in the block's last epilogue
         self._init_image_cross_attention()
         super().to(dtype=dtype)
+        # reference mvd_unet.py:46-52 / image_encoder.py:18-22 load SD2.1 with from_pretrained and THEN seed the
+        # adapters from those weights (attention.py:199-246). A local checkpoint is loaded the same way; a hub name
+        # (no network here) or a missing path leaves RANDOM weights, which is said loudly instead of silently.
+        if isinstance(pretrained_model_name_or_path, (str, os.PathLike)):
+            found = _find_unet_weights(pretrained_model_name_or_path)
+            if found is not None:
+                self.load_base_weights(_read_state_dict(found))
+            else:
+                import warnings
+
+                warnings.warn(f"MultiViewUNet: no local UNet weights under {pretrained_model_name_or_path!r} (this build "
+                              "has no hub access): base UNet, image encoder and the adapters seeded from them are "
+                              "RANDOM-INITIALISED. Call load_base_weights(sd21_unet_state_dict) before use.",
+                              RuntimeWarning, stacklevel=2)
+
+    def load_base_weights(self, state_dict: Dict[str, torch.Tensor], reseed_adapters: bool = True):
+        """Load a diffusers SD2.1 `unet` state dict into the base UNet AND the frozen image-encoder UNet, then re-run
+        the reference's adapter initialisation on all processors (attention.py:199-246: to_q_ref/to_k_ref/to_v_ref/
+        to_out_ref copied from the — now pretrained — attention weights), exactly the order from_pretrained gives
+        the reference. The processors' own keys (`*.processor.*`) are absent from an SD2.1 checkpoint, hence
+        strict=False for them only; any other missing / unexpected key raises."""
+        sd = {k: v for k, v in state_dict.items()}
+        res = self.base_unet.load_state_dict(sd, strict=False)
+        missing = [k for k in res.missing_keys if ".processor." not in k]
+        if missing or res.unexpected_keys:
+            raise RuntimeError(f"load_base_weights: missing {missing[:5]} unexpected {list(res.unexpected_keys)[:5]}")
+        if self.image_encoder is not None:
+            self.image_encoder.unet.load_state_dict(sd, strict=True)
+        if reseed_adapters:
+            with torch.no_grad():
+                for attn in self.attention_layer_map.values():
+                    attn.processor.load_original_weights(attn)
+        return self
 
     # ---- reference mvd_unet.py:106-162 ------------------------------------------------------------------------
     def _init_image_cross_attention(self):

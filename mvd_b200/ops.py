@@ -571,5 +571,10 @@ def advance_step_rows(step_idx: torch.Tensor, coef_table: torch.Tensor, timestep
           "mvd_advance_step_rows")
 
 
+def set_launch_overlap(on: bool) -> None:
+    """Programmatic dependent launch for all kernels of the library (process-wide; see the header)."""
+    check(lib().mvd_set_launch_overlap(int(bool(on))), "mvd_set_launch_overlap")
+
+
 def kernel_launch_count() -> int:
     return int(lib().mvd_kernel_launch_count())

@@ -216,8 +216,13 @@ class DenoiseSession:
         ops.cfg_ddpm_step_table(out, self.latents, self.noise_table, self.cfg, self.guidance, self.coef, self.step_idx)
         self.advance()
 
+    # local batches up to this many UNet samples are launch / latency bound: their kernels are launched with
+    # programmatic dependent launch (measured: +5 % at 1 sample, +1 % at 2, -3 % at 8)
+    LAUNCH_OVERLAP_MAX_BATCH = 2
+
     def capture(self, warmup: int = 2):
         """Warm every cache (weight packs, reference features, K/V) eagerly, then record one step."""
+        ops.set_launch_overlap(self.views * self.cfg <= self.LAUNCH_OVERLAP_MAX_BATCH)
         saved = (self.latents.clone(), self.step_idx.clone(), self.t_dev.clone(),
                  None if self.temb_row is None else self.temb_row.clone())
         side = torch.cuda.Stream()

