@@ -44,6 +44,29 @@ METRIC = "MV denoise steps/s (SD2.1+adapter 512^2, 4 views x CFG 2)"
 GUIDANCE = 3.0
 INFER_STEPS = 50
 FLOPS_PER_STEP = 8.80e12  # 8 samples x 1151.6 GF minus the cached K/V projections
+CROSS_VIEW = False
+
+
+def select_workload(name: str):
+    """c1 (default, the driver's line): BASELINE.json configs[1]/[2]. c3: configs[3] — 8 views at 768^2 (96^2 latents),
+    camera + image conditioning, cross-view reference mode: every view attends over the reference tokens of ALL 8 views
+    (S_kv = 73 728 at the top sites), no CFG; sharded one view per GPU at N = 8."""
+    global VIEWS, LATENT, CFG, WORKLOAD, METRIC, GUIDANCE, FLOPS_PER_STEP, CROSS_VIEW
+    if name == "c1":
+        return
+    if name != "c3":
+        raise SystemExit(f"unknown workload {name}")
+    VIEWS, LATENT, CFG, GUIDANCE, CROSS_VIEW = 8, 96, 1, 1.0, True
+    WORKLOAD = ("configs[3]: one SD2.1 UNet + MV-adapter denoise step, 8 views at 768^2 (96^2 latent), cross-view "
+                "reference attention over all 8 views' tokens (S_kv = 73728 at the top sites), camera + image conditioning")
+    METRIC = "MV denoise steps/s (SD2.1+adapter 768^2, 8 views, cross-view K/V)"
+    from flops import unet_flops
+
+    f = unet_flops(LATENT, skv_factor=VIEWS)
+    # per sample: everything except the step-invariant K/V projections of the reference tokens (half of ref_proj's
+    # S_kv-sized terms: to_k_ref and to_v_ref; they are computed once per object)
+    hw_terms = unet_flops(LATENT, skv_factor=1)["ref_proj"] / 2  # to_q_ref + to_out_ref
+    FLOPS_PER_STEP = VIEWS * (f["base"] + f["ref_attn"] + hw_terms)
 
 
 def peaks():
@@ -95,7 +118,7 @@ def build_pipeline(dev):
 
     torch.manual_seed(0)
     pipe = mvd_b200.create_mvd_pipeline(None, dtype=torch.bfloat16, img_ref_scale=1.0, cam_modulation_strength=1.0,
-                                        matched_batch_cfg=True, device=dev)
+                                        matched_batch_cfg=True, device=dev, cross_view_reference=CROSS_VIEW)
     g = torch.Generator(device=dev).manual_seed(1)
     with torch.no_grad():  # ref branch != original branch
         for n, p in pipe.unet.named_parameters():
@@ -105,7 +128,7 @@ def build_pipeline(dev):
 
 
 def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch: int, use_graph=True, pipe=None,
-                  sharded=None):
+                  sharded=None, emulated=False):
     """The slice of the object this rank owns: views [view0, view0+views_local), CFG branches
     (both if cfg_local == 2, else only `cfg_branch`: 0 = uncond, 1 = cond)."""
     from helpers import synthetic_inputs
@@ -115,20 +138,20 @@ def build_session(dev, views_local: int, view0: int, cfg_local: int, cfg_branch:
         pipe = build_pipeline(dev)
     inp = synthetic_inputs(VIEWS, LATENT, CFG)
     vs = slice(view0, view0 + views_local)
-    text_u, text_c = inp["text"][:VIEWS][vs], inp["text"][VIEWS:][vs]
+    text_u, text_c = inp["text"][:VIEWS][vs], inp["text"][VIEWS * (CFG - 1):][vs]
     unet = pipe.unet
     # reference features are computed over ALL views on every rank (step-invariant; normalisation statistics
     # couple the batch, attention.py:95-103), this rank's processors then use the rows of its own samples
     unet.shard = None
     if (views_local * cfg_local < VIEWS * CFG) if sharded is None else sharded:
         unet.shard = dict(view0=view0, views_local=views_local, views_total=VIEWS, cfg_total=CFG, cfg_branch=cfg_branch,
-                          ie_text=inp["text"][VIEWS:].to(dev).contiguous())
+                          ie_text=inp["text"][VIEWS * (CFG - 1):].to(dev).contiguous(), emulated=bool(emulated))
     if cfg_local == 2:
         sess = DenoiseSession(pipe, text_c, INFER_STEPS, GUIDANCE, text_u, inp["source_camera"][vs],
                               inp["target_camera"][vs], inp["source_latents"], LATENT, use_cuda_graph=use_graph,
                               pos_proj=inp["pos_proj"])
     else:
-        sess = DenoiseSession(pipe, text_c if cfg_branch else text_u, INFER_STEPS, 1.0, None, inp["source_camera"][vs],
+        sess = DenoiseSession(pipe, text_c if (cfg_branch or CFG == 1) else text_u, INFER_STEPS, 1.0, None, inp["source_camera"][vs],
                               inp["target_camera"][vs], inp["source_latents"], LATENT, use_cuda_graph=use_graph,
                               pos_proj=inp["pos_proj"])
     noises = torch.stack([torch.randn(VIEWS, 4, LATENT, LATENT, generator=torch.Generator().manual_seed(6 + i))
@@ -147,6 +170,11 @@ def attention_roofline(dev, pk, how):
     g = torch.Generator(device=dev).manual_seed(3)
     qkv = torch.randn(B, S, 3 * C, device=dev, generator=g).to(torch.bfloat16)
     q, k, v = qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:]
+    s_kv = S
+    if CROSS_VIEW:  # the reference branch: one K/V sequence of all views' tokens shared by every sample
+        s_kv = VIEWS * S
+        kv = torch.randn(1, s_kv, 2 * C, device=dev, generator=g).to(torch.bfloat16)
+        k, v = kv[:, :, :C].expand(B, -1, -1), kv[:, :, C:].expand(B, -1, -1)
     out = torch.empty(B, S, C, device=dev, dtype=torch.bfloat16)
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
     def timed(**kw):
@@ -167,15 +195,16 @@ def attention_roofline(dev, pk, how):
     # inside the step this site runs as two concurrent launches (self / reference branch on two streams) that fill each
     # other's last wave, so neither splits (co_units): the same kernel, timed alone in that configuration
     ms_in_step_cfg = timed(co_units=ops.attention_units(B, H, S))
-    flops = 4.0 * S * S * C * B
+    flops = 4.0 * S * s_kv * C * B
     achieved = flops / (ms * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
     traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    return {"kernel": "attn_pair_kernel (B=8,h=5,Sq=Skv=4096,d=64)", "bound": "tensor", "achieved": round(achieved, 1),
+    if not CROSS_VIEW:  # the committed ncu capture is of the configs[1] shape
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    return {"kernel": f"attn_pair_kernel (B={B},h={H},Sq={S},Skv={s_kv},d=64)", "bound": "tensor", "achieved": round(achieved, 1),
             "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
             "peak_source": f"{how} burst bf16 GEMM", "ms_per_launch": round(ms, 4),
             "flops_per_launch": flops,
@@ -287,7 +316,8 @@ def build_rank_session(dev, sp, pipe, use_graph, guidance=GUIDANCE):
     from mvd_b200 import dist as mdist
 
     _, s2, inp, noises = build_session(dev, sp["views_local"], sp["view0"], sp["cfg_local"], sp["cfg_branch"],
-                                       use_graph=use_graph, pipe=pipe, sharded=sp["world"] > 1)
+                                       use_graph=use_graph, pipe=pipe, sharded=sp["world"] > 1,
+                                       emulated=sp.get("emulated", False))
     if sp["cfg_local"] == 1 and CFG == 2:
         if sp.get("emulated"):  # no partner rank: the pair's other prediction is a copy of ours (same kernels, no NCCL)
             from mvd_b200 import ops
@@ -482,12 +512,12 @@ def run_ours(args):
         result["line"]["emulated_rank_of"] = args.shard_of
     if world == 1 and rank == 0 and args.shard_of == 1:
         result["line"]["roofline"] = attention_roofline(dev, pk, how)
-        if not args.no_parity:
+        if not args.no_parity and args.workload == "c1":
             try:
                 result["line"]["parity"] = parity_check(pipe, timed_latents, dev)
             except Exception as exc:  # noqa: BLE001
                 result["line"]["parity"] = {"error": f"{type(exc).__name__}: {exc}"[:300], "ok": False}
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.workload == "c1":
             result["line"]["cpu_baseline"] = cpu_baseline()[0]
     finished.set()
     emit()
@@ -537,12 +567,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c3"],
+                    help="c1 = BASELINE configs[1]/[2] (default, the driver's line); c3 = configs[3]: 8 views at 768^2, cross-view K/V")
     ap.add_argument("--shard-of", type=int, default=1, help="single GPU: run rank 0's share of an N-rank view-sharded job "
                     "(no NCCL; for profiling the per-rank step)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed model (N = 1)")
     ap.add_argument("--no-replicas", action="store_true", help="N > 1: skip the sample-parallel (replica) side figure")
     ap.add_argument("--profile", action="store_true", help="run one eager step inside cudaProfilerStart/Stop and exit")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -167,6 +167,12 @@ int mvd_layernorm_f32(const float* x, const void* gamma, const void* beta, float
 int64_t mvd_refnorm_workspace_floats(int channels);
 int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels, int per_pixel, float* workspace,
                      int64_t workspace_floats, void* stream);
+/* per_pixel = 0 form for a reference that is `replication` IDENTICAL copies of x along the batch (cross-view mode: every
+ * sample gets the tokens of all views, src/models/attention.py:190-197 leaves a 3-D reference as is): the statistics
+ * of the replicated tensor (mean unchanged, unbiased std with rep*rows - 1 in the denominator) without materialising
+ * it; out holds ONE normalised copy, shared by all samples through the attention op's zero batch stride. */
+int mvd_refnorm_replicated_bf16(const void* x, void* out, int batch, int seq, int channels, int per_pixel,
+                                int replication, float* workspace, int64_t workspace_floats, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------
  * Elementwise / embedding / layout kernels, csrc/elementwise.cu

@@ -64,6 +64,7 @@ _SIGNATURES = {
     "mvd_layernorm_f32": (_I, [_P, _P, _P, _P, _I, _I, _F, _I, _P]),
     "mvd_refnorm_workspace_floats": (_L, [_I]),
     "mvd_refnorm_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P, _L, _P]),
+    "mvd_refnorm_replicated_bf16": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _L, _P]),
     "mvd_film_bf16": (_I, [_P, _P, _P, _I, _I, _I, _I, _F, _P]),
     "mvd_small_linear_f32": (_I, [_P, _L, _P, _P, _P, _L, _I, _I, _I, _I, _I, _P]),
     "mvd_timestep_embedding_f32": (_I, [_P, _I, _P, _I, _I, _P]),

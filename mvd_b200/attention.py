@@ -55,6 +55,21 @@ def _branch_stream(device: torch.device) -> "torch.cuda.Stream":
     return s
 
 
+class SharedReference:
+    """A 3-D reference [B, S_kv, C] whose B batch entries are IDENTICAL (cross-view mode, BASELINE configs[3]: every
+    sample attends over the tokens of all views), held as ONE copy `tokens` [1, S_kv, C] + the batch size it stands
+    for. The reference normalisation (attention.py:95-103, statistics over (batch, sequence) of the raw tensor) is
+    computed for the replicated tensor without materialising it, K/V are projected once and every sample reads them
+    through a zero batch stride."""
+
+    __slots__ = ("tokens", "replication")
+
+    def __init__(self, tokens: torch.Tensor, replication: int):
+        if tokens.dim() != 3 or tokens.shape[0] != 1:
+            raise ValueError("SharedReference holds one copy: tokens must be [1, S_kv, C]")
+        self.tokens, self.replication = tokens, int(replication)
+
+
 class ImageCrossAttentionProcessor(nn.Module):
     def __init__(self, name: str, query_dim: int, heads: int, dim_head: int = 64, dropout: float = 0.0,
                  img_ref_scale: float = 0.3):
@@ -116,9 +131,9 @@ class ImageCrossAttentionProcessor(nn.Module):
         return hit[1]
 
     # ---- step-invariant reference K/V ---------------------------------------------------------------------
-    def _reference_kv(self, ref: torch.Tensor, pk) -> torch.Tensor:
+    def _reference_kv(self, ref: torch.Tensor, pk, replication: int = 1) -> torch.Tensor:
         """[B_ref * S_kv, 2C] = [to_k_ref(r) | to_v_ref(r)], r = normalised reference (attention.py:95-132)."""
-        key = (ref.data_ptr(), ref._version, tuple(ref.shape), tuple(ref.stride()), ref.dtype)
+        key = (ref.data_ptr(), ref._version, tuple(ref.shape), tuple(ref.stride()), ref.dtype, replication)
         cached = self.__dict__.get("_ref_cache")
         if cached is not None and cached[0] == key:
             return cached[1]
@@ -139,7 +154,9 @@ class ImageCrossAttentionProcessor(nn.Module):
             raise ValueError(f"reference features must be 3-D or 4-D, got {ref.dim()}-D")
         if tok.shape[-1] != self.query_dim:
             raise ValueError(f"{self.name}: reference has {tok.shape[-1]} channels, expected {self.query_dim}")
-        normed = ops.refnorm(tok.contiguous(), per_pixel=per_pixel)
+        if replication != 1 and per_pixel:
+            raise ValueError("a shared (replicated) reference must be 3-D")
+        normed = ops.refnorm(tok.contiguous(), per_pixel=per_pixel, replication=replication)
         b, s, c = normed.shape
         kv = ops.linear(normed.view(b * s, c), pk["wkv_ref"])
         self.__dict__["_ref_cache"] = (key, kv, ref)  # hold `ref` so its storage cannot be recycled under the key
@@ -189,18 +206,29 @@ class ImageCrossAttentionProcessor(nn.Module):
         b, s, c = hidden_states.shape
         hs2d = hidden_states.reshape(b * s, c)
         ref_t = ref_hidden_states[self.name]
-        kv_ref = self._reference_kv(ref_t, pk)
-        if ref_batch_index is not None:
+        shared = isinstance(ref_t, SharedReference)
+        if shared:
+            if ref_t.replication < b:
+                raise ValueError(f"{self.name}: the shared reference stands for {ref_t.replication} samples, query "
+                                 f"batch is {b}")
+            kv_ref = self._reference_kv(ref_t.tokens, pk, replication=ref_t.replication)
+        else:
+            kv_ref = self._reference_kv(ref_t, pk)
+        if ref_batch_index is not None and not shared:
             # view-sharded execution (mvd_b200/dist.py): K/V were normalised + projected over the FULL reference
             # batch; this rank attends with the rows of its own samples
             kv_ref = self._gather_batch(kv_ref, ref_t.shape[0], ref_batch_index)
         rows = kv_ref.shape[0]
-        if rows % b:
-            raise ValueError(f"{self.name}: {rows} reference tokens do not split over query batch {b}")
-        # reference attention.py:130,132: key.view(batch_size, -1, heads, dim_head) — a flat re-view by the QUERY
-        # batch (with CFG and an un-repeated reference each sample sees a different half of the tokens)
-        k_ref = kv_ref[:, :c].view(b, rows // b, c)
-        v_ref = kv_ref[:, c:].view(b, rows // b, c)
+        if shared:  # every sample reads the one K/V copy (zero batch stride in the attention kernel's tensor maps)
+            k_ref = kv_ref[:, :c].unsqueeze(0).expand(b, rows, c)
+            v_ref = kv_ref[:, c:].unsqueeze(0).expand(b, rows, c)
+        else:
+            if rows % b:
+                raise ValueError(f"{self.name}: {rows} reference tokens do not split over query batch {b}")
+            # reference attention.py:130,132: key.view(batch_size, -1, heads, dim_head) — a flat re-view by the QUERY
+            # batch (with CFG and an un-repeated reference each sample sees a different half of the tokens)
+            k_ref = kv_ref[:, :c].view(b, rows // b, c)
+            v_ref = kv_ref[:, c:].view(b, rows // b, c)
         res2d = residual.reshape(b * s, c) if residual is not None else None
         scale = self.dim_head ** -0.5
 

@@ -677,9 +677,10 @@ refnorm_col_sum_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int C,
 #pragma unroll
   for (int k = 0; k < 8; ++k) partial[static_cast<int64_t>(chunk) * C + c + k] = acc[k];
 }
-// reduce partial[chunks][C] -> out[C] = f(sum): mode 0: mean = sum / rows ; mode 1: 0.5 / clamp(sqrt(sum/(rows-1)))
+// reduce partial[chunks][C] -> out[C] = f(sum): mode 0: mean = sum / rows ; mode 1: 0.5 / clamp(sqrt(rep * sum / (rep * rows - 1)))
+// (rep identical copies of the rows: the statistics of the replicated tensor without materialising it)
 __global__ void refnorm_col_finalize_kernel(const float* __restrict__ partial, int chunks, int C, double rows, int mode,
-                                            float* __restrict__ out) {
+                                            float* __restrict__ out, double rep) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double s = 0.0;
@@ -687,7 +688,7 @@ __global__ void refnorm_col_finalize_kernel(const float* __restrict__ partial, i
   if (mode == 0) {
     out[c] = static_cast<float>(s / rows);
   } else {
-    const float stdv = fmaxf(static_cast<float>(sqrt(s / (rows - 1.0))), 1e-6f);
+    const float stdv = fmaxf(static_cast<float>(sqrt(rep * s / (rep * rows - 1.0))), 1e-6f);
     out[c] = 0.5f / stdv;
   }
 }
@@ -874,7 +875,14 @@ int64_t mvd_refnorm_workspace_floats(int channels) { return static_cast<int64_t>
 
 int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels, int per_pixel, float* workspace,
                      int64_t workspace_floats, void* stream) {
+  return mvd_refnorm_replicated_bf16(x, out, batch, seq, channels, per_pixel, 1, workspace, workspace_floats, stream);
+}
+
+int mvd_refnorm_replicated_bf16(const void* x, void* out, int batch, int seq, int channels, int per_pixel,
+                                int replication, float* workspace, int64_t workspace_floats, void* stream) {
   using namespace mvd;
+  MVD_CHECK(replication >= 1 && (replication == 1 || !per_pixel),
+            "refnorm: replication applies to the 3-D (per-channel) form only");
   MVD_CHECK(batch > 0 && seq > 0 && channels > 0 && channels % 8 == 0, "refnorm: bad shape B=%d S=%d C=%d", batch, seq,
             channels);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -889,7 +897,7 @@ int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels,
   }
   MVD_CHECK(workspace_floats >= mvd_refnorm_workspace_floats(channels), "refnorm: workspace too small");
   const int64_t rows = static_cast<int64_t>(batch) * seq;
-  MVD_CHECK(rows > 1, "refnorm: unbiased std needs more than one row");
+  MVD_CHECK(rows * replication > 1, "refnorm: unbiased std needs more than one row");
   const int chunks = rows < RN_CHUNKS ? static_cast<int>(rows) : RN_CHUNKS;
   float* partial = workspace;
   float* mean = workspace + static_cast<int64_t>(RN_CHUNKS) * channels;
@@ -898,10 +906,11 @@ int mvd_refnorm_bf16(const void* x, void* out, int batch, int seq, int channels,
   dim3 grid(chunks, (channels / 8 + tx - 1) / tx);
   refnorm_col_sum_kernel<<<grid, tx, 0, st>>>(xx, rows, channels, nullptr, partial);
   refnorm_col_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(partial, chunks, channels,
-                                                                      static_cast<double>(rows), 0, mean);
+                                                                      static_cast<double>(rows), 0, mean, 1.0);
   refnorm_col_sum_kernel<<<grid, tx, 0, st>>>(xx, rows, channels, mean, partial);
   refnorm_col_finalize_kernel<<<(channels + 127) / 128, 128, 0, st>>>(partial, chunks, channels,
-                                                                      static_cast<double>(rows), 1, scale);
+                                                                      static_cast<double>(rows), 1, scale,
+                                                                      static_cast<double>(replication));
   const int64_t nvec = rows * channels / 8;
   refnorm_col_apply_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, st>>>(xx, oo, nvec, channels, mean,
                                                                                       scale);

@@ -245,11 +245,28 @@ class MultiViewUNet(nn.Module):
                                      "re-view of un-repeated features (attention.py:130-132) mixes the samples of "
                                      "different ranks")
                 sharded = shard["views_local"] * cfg_local < shard["views_total"] * cfg_total
-            if sharded:  # features for ALL views (batch-coupled normalisation), conditional text of all views
+            xview_sharded = sharded and self.cross_view_reference
+            if sharded and not xview_sharded:
+                # features for ALL views (batch-coupled normalisation), conditional text of all views
                 ie_text = self._prepare_text(shard["ie_text"].to(device=dev), batch_size)
-            features = self.image_encoder(latents=source_image_latents.to(device=dev), text_embeddings=ie_text,
-                                          timestep=0)
-            if sharded:
+            src_lat = source_image_latents.to(device=dev)
+            emulated = bool(shard.get("emulated")) if shard is not None else False
+            if xview_sharded:
+                # cross-view mode: this rank encodes only ITS views; the token sets are all-gathered below
+                # (emulated = a single-GPU stand-in for one rank: it encodes all views itself, no collective)
+                ie_text = self._prepare_text(shard["ie_text"].to(device=dev), batch_size)
+                if not emulated:
+                    v0, vl = shard["view0"], shard["views_local"]
+                    src_lat = src_lat[v0:v0 + vl]
+                    ie_text = ie_text[v0:v0 + vl].contiguous()
+            features = self.image_encoder(latents=src_lat, text_embeddings=ie_text, timestep=0)
+            if xview_sharded:
+                cfg_total = int(shard.get("cfg_total", 2))
+                world = 1 if emulated else shard["views_total"] // shard["views_local"]
+                features = self._cross_view_features(features, shard["views_total"] * cfg_total,
+                                                     gather_group=shard.get("group"), world=world)
+                ref_batch_index = None
+            elif sharded:
                 cfg_total = shard.get("cfg_total", 2)
                 if self.matched_batch_cfg and cfg_total > 1:
                     features = self._repeat_features(features, cfg_total)
@@ -320,11 +337,15 @@ class MultiViewUNet(nn.Module):
         self.__dict__["_rep_cache"] = (key, rep, features)
         return rep
 
-    def _cross_view_features(self, features, batch: int):
-        """[V, C, H, W] per site -> the 3-D reference [batch, V*HW, C]: all views' tokens, the same for every sample.
-        (The reference-literal tensor: one copy per sample, so that the normalisation statistics of
-        attention.py:95-103 count exactly what they would count there.) Cached with the features."""
-        key = (id(features), batch)
+    def _cross_view_features(self, features, batch: int, gather_group=None, world: int = 1):
+        """[V, C, H, W] per site -> the 3-D reference of attention.py:95-132 holding the tokens of ALL views, the same
+        for every one of the `batch` samples: ONE copy [1, V*HW, C] + its replication factor (SharedReference), never
+        the [batch, V*HW, C] tensor itself. View-sharded ranks hold only their own views' features: those are
+        all-gathered over NVLink (NCCL) — once per object, the features are step-invariant — so that every rank
+        normalises and projects exactly the token set a single GPU would. Cached with the features."""
+        from .attention import SharedReference
+
+        key = (id(features), batch, world)
         cached = self.__dict__.get("_xview_cache")
         if cached is not None and cached[0] == key and cached[2] is features:
             return cached[1]
@@ -332,8 +353,14 @@ class MultiViewUNet(nn.Module):
         for name, f in features.items():
             if isinstance(f, tuple):
                 f = f[0]
-            v = nhwc_view(f)  # [V, H, W, C], dense
-            out[name] = v.reshape(1, -1, v.shape[-1]).repeat(batch, 1, 1)
+            v = nhwc_view(f).contiguous()  # [V_local, H, W, C]
+            if world > 1:
+                import torch.distributed as dist
+
+                full = torch.empty((world * v.shape[0],) + tuple(v.shape[1:]), device=v.device, dtype=v.dtype)
+                dist.all_gather_into_tensor(full, v, group=gather_group)  # rank order == view order (shard_plan)
+                v = full
+            out[name] = SharedReference(v.reshape(1, -1, v.shape[-1]), batch)
         self.__dict__["_xview_cache"] = (key, out, features)
         return out
 
@@ -378,7 +405,7 @@ def create_mvd_pipeline(pretrained_model_name_or_path=None, dtype: torch.dtype =
                         img_ref_scale: float = 0.25, cam_modulation_strength: float = 1.0, cam_output_dim: int = 1024,
                         cam_hidden_dim: int = 512, simple_cam_encoder: bool = False, cache_dir=None,
                         scheduler_config: Optional[Dict[str, Any]] = None, matched_batch_cfg: bool = False,
-                        device: Optional[str] = None):
+                        device: Optional[str] = None, cross_view_reference: bool = False):
     """reference mvd_unet.py:388-453: DDPM scheduler rebuilt on SNR-shifted (interpolated, scale 6) betas + the
     multi-view UNet. Text encoder and VAE are outside this library's scope (pass prompt_embeds / latents)."""
     from .pipeline import MVDPipeline
@@ -397,7 +424,8 @@ def create_mvd_pipeline(pretrained_model_name_or_path=None, dtype: torch.dtype =
                                 cam_output_dim=cam_output_dim, cam_hidden_dim=cam_hidden_dim,
                                 simple_cam_encoder=simple_cam_encoder,
                                 use_camera_conditioning=use_camera_conditioning,
-                                use_image_conditioning=use_image_conditioning, matched_batch_cfg=matched_batch_cfg)
+                                use_image_conditioning=use_image_conditioning, matched_batch_cfg=matched_batch_cfg,
+                                cross_view_reference=cross_view_reference)
     mv_unet = mv_unet.to(device=device, dtype=dtype)
     pipeline = MVDPipeline(unet=mv_unet, scheduler=scheduler)
     pipeline.use_camera_conditioning = use_camera_conditioning

@@ -372,16 +372,18 @@ def layernorm_f32(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return out
 
 
-def refnorm(x: torch.Tensor, per_pixel: bool, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x: bf16 [B,S,C] channels-last reference features -> normalised (attention.py:95-103 semantics)."""
+def refnorm(x: torch.Tensor, per_pixel: bool, out: Optional[torch.Tensor] = None, replication: int = 1) -> torch.Tensor:
+    """x: bf16 [B,S,C] channels-last reference features -> normalised (attention.py:95-103 semantics).
+    replication > 1 (3-D form only): x stands for that many identical copies along the batch; the statistics are those
+    of the replicated tensor, ONE normalised copy is returned."""
     _contig(x, "x")
     B, S, C = x.shape
     if out is None:
         out = torch.empty_like(x)
     need = lib().mvd_refnorm_workspace_floats(C)
     ws = _workspace(x.device, need, "refnorm")
-    check(lib().mvd_refnorm_bf16(_p(x), _p(out), B, S, C, int(per_pixel), _p(ws), ws.numel(), _stream()),
-          "mvd_refnorm_bf16")
+    check(lib().mvd_refnorm_replicated_bf16(_p(x), _p(out), B, S, C, int(per_pixel), int(replication), _p(ws),
+                                            ws.numel(), _stream()), "mvd_refnorm_replicated_bf16")
     return out
 
 

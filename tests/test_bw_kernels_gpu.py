@@ -86,6 +86,23 @@ def test_refnorm_channel(B, S, C):
     _close(ops.refnorm(x, per_pixel=False), r, f"refnorm channel {B}x{S}x{C}", atol=1e-2)
 
 
+@pytest.mark.parametrize("S,C,rep", [(4 * 256, 320, 8), (77, 64, 2), (2048, 1280, 16)])
+def test_refnorm_replicated_reference(S, C, rep):
+    """One copy [1,S,C] standing for `rep` identical batch entries (cross-view mode): same result as normalising the
+    materialised [rep,S,C] tensor the way attention.py:95-103 does (mean over (0,1), UNBIASED std over rep*S values)."""
+    from mvd_b200 import ops
+
+    x = _r(1, S, C, seed=1, shift=0.3, scale=0.9)
+    xf = x.float().repeat(rep, 1, 1)
+    r = xf - xf.mean(dim=(0, 1), keepdim=True)
+    r = r / torch.clamp(r.std(dim=(0, 1), keepdim=True), min=1e-6) * 0.5
+    got = ops.refnorm(x, per_pixel=False, replication=rep)
+    assert got.shape == (1, S, C)
+    _close(got, r[:1], f"refnorm replicated x{rep} {S}x{C}", atol=1e-2)
+    with pytest.raises(Exception):
+        ops.refnorm(x, per_pixel=True, replication=rep)
+
+
 def test_refnorm_constant_input_clamps():
     from mvd_b200 import ops
 

@@ -71,6 +71,64 @@ def _worker(rank, world, port, ret):
     os._exit(0)  # NCCL teardown after a captured collective has been seen to hang on this stack
 
 
+def _xview_worker(rank, world, port, ret):
+    import signal
+
+    signal.alarm(240)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+
+    import mvd_b200
+    from helpers import metrics, synthetic_inputs
+    from mvd_b200 import dist as mdist
+    from mvd_b200.unet import tiny_config
+
+    torch.cuda.set_device(rank)
+    dev = f"cuda:{rank}"
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    torch.manual_seed(0)
+    m = mvd_b200.MultiViewUNet(tiny_config(), dtype=torch.bfloat16, img_ref_scale=1.0, cam_modulation_strength=1.0,
+                               matched_batch_cfg=True, cross_view_reference=True).to(dev, dtype=torch.bfloat16).eval()
+    V, L = 2, 16
+    inp = synthetic_inputs(V, L, cfg=1, text_dim=64)
+    m.camera_encoder.set_positional_projection(inp["pos_proj"])
+    x, text, src = inp["latents"].to(dev), inp["text"].to(dev), inp["source_latents"].to(dev)
+    with torch.no_grad():
+        full = m(x, 621, text, inp["source_camera"].to(dev), inp["target_camera"].to(dev), src).sample
+        p = mdist.shard_plan(V, 1, world, rank)
+        vs = slice(p["view0"], p["view0"] + p["views_local"])
+        # every rank encodes only its own view; the per-site reference tokens travel by NCCL all_gather
+        m.shard = dict(view0=p["view0"], views_local=p["views_local"], views_total=V, cfg_total=1, cfg_branch=0,
+                       ie_text=text.contiguous())
+        y = m(x[vs].contiguous(), 621, text[vs].contiguous(), inp["source_camera"][vs].to(dev),
+              inp["target_camera"][vs].to(dev), src).sample
+    torch.cuda.synchronize()
+    mm = metrics(y, full[vs])
+    ret[rank] = (mm["rel"], mm["cos"])
+    dist.barrier()
+    torch.cuda.synchronize()
+    os._exit(0)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_cross_view_reference_all_gather_matches_single_gpu():
+    """BASELINE configs[3] / north-star collective: views split over ranks, the step-invariant per-view reference
+    tokens of all 16 sites all-gathered once (NCCL over NVLink); each rank's prediction equals the rows of the
+    single-GPU cross-view forward."""
+    import torch.multiprocessing as mp
+
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    ctx = mp.spawn(_xview_worker, args=(2, _free_port(), ret), nprocs=2, join=False)
+    for p in ctx.processes:
+        p.join(300)
+    got = dict(ret)
+    assert len(got) == 2, f"ranks did not finish: {got}"
+    for rank, (rel, cos) in got.items():
+        print(f"rank {rank}: normalised max-abs {rel:.3e} cos {cos:.6f}")
+        assert rel <= 2e-2 and cos >= 0.9999, (rank, rel, cos)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_cfg_pair_sharded_step_matches_single_gpu():
     import torch.multiprocessing as mp
