@@ -225,22 +225,34 @@ __global__ void camera_front_kernel(const float* __restrict__ src, const float* 
 // fused in (src/models/mvd_unet.py:256-258 applies the "output" modulator to the input sample) and the CFG
 // duplication folded into the index (sample n reads latent n % n_lat). Output NHWC bf16.
 // ------------------------------------------------------------------------------------------------
-constexpr int CIN_ROWS = 4;  // output rows per block: the [Cout][36] weight tile in smem is reused 4 x 32 pixels
+// Lanes are PIXELS (32 consecutive pixels of an image per warp), a thread keeps its pixel's 36 modulated inputs in
+// registers and produces Cout/4 output channels, 8 at a time, from an fp32 [36][Cout] copy of the weights in shared
+// memory (two broadcast LDS.128 per 8 FMAs). Round 1's form (channel vectors across lanes, 2-way bank conflicts on
+// every weight load, [Cout][36] -> [36][Cout] transpose with a 32-way conflict) took 126 us at 8 x 64 x 64.
+constexpr int CIN_TP = 64;  // pixels per block (two warps of pixels x four channel quarters)
 __global__ void __launch_bounds__(256)
 conv_in_kernel(const float* __restrict__ lat, int n_lat, const float* __restrict__ mod /*[V, 8] or null*/, int V,
                float strength, const __nv_bfloat16* __restrict__ w /*[Cout, 3,3, 4]*/,
                const __nv_bfloat16* __restrict__ bias, __nv_bfloat16* __restrict__ out, int H, int W, int Cout) {
   pdl_wait();
   pdl_launch_dependents();
-  extern __shared__ float s_w[];  // [36][Cout] (tap-major: conflict-free reads of 8 consecutive channels) + bias[Cout]
-  float* s_b = s_w + Cout * 36;
-  for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) {
-    const int co = i / 36, tap = i % 36;
-    s_w[tap * Cout + co] = __bfloat162float(w[i]);
-  }
+  extern __shared__ float s_w[];                                             // [36][Cout] fp32, tap-major
+  float* s_b = s_w + Cout * 36;                                              // [Cout]
+  __nv_bfloat16* s_raw = reinterpret_cast<__nv_bfloat16*>(s_b + Cout);       // [Cout][36] as stored
+  for (int i = threadIdx.x; i < Cout * 36 / 8; i += blockDim.x)
+    reinterpret_cast<uint4*>(s_raw)[i] = reinterpret_cast<const uint4*>(w)[i];
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_b[i] = __bfloat162float(bias[i]);
-  __shared__ float s_in[4][CIN_ROWS + 2][34];  // 4 channels x (rows + halo) x (32 + 2) columns
-  const int n = blockIdx.z, y0 = blockIdx.y * CIN_ROWS, x0 = blockIdx.x * 32;
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * 36; i += blockDim.x) {
+    const int tap = i / Cout, co = i - tap * Cout;
+    s_w[i] = __bfloat162float(s_raw[co * 36 + tap]);
+  }
+  const int n = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hw = H * W;
+  const int pix = blockIdx.x * CIN_TP + (warp >> 2) * 32 + lane;
+  const bool valid = pix < hw;
+  const int y = valid ? pix / W : 0, x = valid ? pix - (pix / W) * W : 0;
   float sc[4], sh[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
@@ -252,36 +264,37 @@ conv_in_kernel(const float* __restrict__ lat, int n_lat, const float* __restrict
       sh[c] = m[4 + c] * strength;
     }
   }
-  const float* lb = lat + static_cast<int64_t>(n % n_lat) * 4 * H * W;
-  for (int i = threadIdx.x; i < 4 * (CIN_ROWS + 2) * 34; i += blockDim.x) {
-    const int c = i / ((CIN_ROWS + 2) * 34), r = (i / 34) % (CIN_ROWS + 2), col = i % 34;
-    const int yy = y0 + r - 1, xx = x0 + col - 1;
-    float v = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) v = lb[(static_cast<int64_t>(c) * H + yy) * W + xx] * sc[c] + sh[c];
-    s_in[c][r][col] = v;
-  }
+  // the pixel's 3x3x4 neighbourhood (zero padding applies to the MODULATED sample), tap-major like the weights
+  const float* lb = lat + static_cast<int64_t>(n % n_lat) * 4 * hw;
+  float in[36];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int yy = y + ky - 1, xx = x + kx - 1;
+      const bool inb = valid && yy >= 0 && yy < H && xx >= 0 && xx < W;
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        in[(ky * 3 + kx) * 4 + c] = inb ? fmaf(__ldg(lb + static_cast<int64_t>(c) * hw + yy * W + xx), sc[c], sh[c]) : 0.f;
+    }
   __syncthreads();
-  // thread -> 8 consecutive output channels of one pixel
-  const int nvec = Cout / 8;
-  for (int i = threadIdx.x; i < CIN_ROWS * 32 * nvec; i += blockDim.x) {
-    const int cv = (i % nvec) * 8, px = (i / nvec) % 32, ry = i / (nvec * 32);
-    if (x0 + px >= W || y0 + ry >= H) continue;
+  const int cq = Cout >> 2;  // channels per warp quarter (host checks Cout % 32 == 0)
+  const int c_begin = (warp & 3) * cq;
+  __nv_bfloat16* op = out + (static_cast<int64_t>(n) * hw + pix) * Cout;
+  for (int cv = c_begin; cv < c_begin + cq; cv += 8) {
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = s_b[cv + k];
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float v = s_in[c][ry + ky][px + kx];
-          const float* wp = s_w + ((ky * 3 + kx) * 4 + c) * Cout + cv;
-          const float4 w0 = *reinterpret_cast<const float4*>(wp), w1 = *reinterpret_cast<const float4*>(wp + 4);
-          acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
-          acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
-        }
-    *reinterpret_cast<uint4*>(out + ((static_cast<int64_t>(n) * H + y0 + ry) * W + x0 + px) * Cout + cv) = ew_pack8(acc);
+    for (int k = 0; k < 36; ++k) {
+      const float4 w0 = *reinterpret_cast<const float4*>(s_w + k * Cout + cv);
+      const float4 w1 = *reinterpret_cast<const float4*>(s_w + k * Cout + cv + 4);
+      const float v = in[k];
+      acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]); acc[2] = fmaf(v, w0.z, acc[2]);
+      acc[3] = fmaf(v, w0.w, acc[3]); acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+      acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+    }
+    if (valid) *reinterpret_cast<uint4*>(op + cv) = ew_pack8(acc);
   }
 }
 
@@ -542,10 +555,11 @@ int mvd_conv_in_f32_bf16(const float* latents, int n_latents, const float* mod, 
   using namespace mvd;
   MVD_CHECK(n_img > 0 && n_latents > 0 && h > 0 && wdt > 0 && c_out % 8 == 0 && c_out <= 1024,
             "conv_in: bad shape Cout=%d", c_out);
-  const size_t smem = static_cast<size_t>(c_out) * 37 * sizeof(float);
+  MVD_CHECK(c_out % 32 == 0, "conv_in: Cout (=%d) must be a multiple of 32", c_out);
+  const size_t smem = static_cast<size_t>(c_out) * 37 * sizeof(float) + static_cast<size_t>(c_out) * 36 * 2;
   // per call: cheap, and correct for every device a process may touch
-  MVD_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  MVD_CUDA(launch_pdl(conv_in_kernel, dim3((wdt + 31) / 32, (h + CIN_ROWS - 1) / CIN_ROWS, n_img), dim3(256), smem,
+  MVD_CUDA(cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  MVD_CUDA(launch_pdl(conv_in_kernel, dim3((h * wdt + CIN_TP - 1) / CIN_TP, n_img), dim3(256), smem,
                       static_cast<cudaStream_t>(stream), latents, n_latents, mod, n_cam > 0 ? n_cam : 1, strength,
                       static_cast<const __nv_bfloat16*>(w), static_cast<const __nv_bfloat16*>(bias),
                       static_cast<__nv_bfloat16*>(out), h, wdt, c_out));
