@@ -478,7 +478,8 @@ def run_ours(args):
         "gpu_launches": int(sess.launches_per_step * args.steps * world),
         "launches_per_step": int(sess.launches_per_step),
         "step_tflops": round(FLOPS_PER_STEP * steps_per_s / 1e12, 1),
-        "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 / (world * pk["bf16_tflops_sustained"]), 4),
+        "step_frac_of_sustained_peak": round(FLOPS_PER_STEP * steps_per_s / 1e12 /
+                                             (max(world, args.shard_of) * pk["bf16_tflops_sustained"]), 4),
     }
 
     # ---- N > 1: the zero-communication replica mode (configs[4]) as a side figure

@@ -144,6 +144,26 @@ class MultiViewUNet(nn.Module):
                     attn.processor.load_original_weights(attn)
         return self
 
+    _CACHE_KEYS = ("_pack_cache", "_ref_cache", "_gather_cache", "_ln_cache", "_ctx_cache", "_feat_cache",
+                   "_text_cache", "_shard_idx", "_rep_cache", "_xview_cache", "_emb_cache", "_mod_cache", "_film_cache")
+
+    def invalidate_caches(self):
+        """Drop every step-invariant cache (weight packs, folded-LayerNorm packs, reference / text K/V, frozen-UNet
+        features, camera embedding and FiLM coefficients) of this model, its image encoder, its camera encoder and all
+        processors. The caches key on (data_ptr, _version) of their inputs, which the raw-pointer kernels of
+        libmvd_b200 never bump: call this after refreshing such an input IN PLACE through ops.* (or an `out=` buffer),
+        and `DenoiseSession.invalidate()` on any session whose captured step read the old tensors."""
+        seen = 0
+        owners = [m for m in self.modules()]
+        owners += [getattr(a, "processor", None) for a in getattr(self, "attention_layer_map", {}).values()]
+        for owner in owners:
+            if owner is None:
+                continue
+            for key in self._CACHE_KEYS:
+                if owner.__dict__.pop(key, None) is not None:
+                    seen += 1
+        return seen
+
     # ---- reference mvd_unet.py:106-162 ------------------------------------------------------------------------
     def _init_image_cross_attention(self):
         self.attention_layer_map = {}

@@ -7,8 +7,9 @@ Out of scope: tokenizer + CLIP text encoder an
 `prompt_embeds` (and `negative_prompt_embeds` for CFG) and `source_image_latents`; the result is the final
 latents (`output_type="latent"`). Asking for prompts / images / PIL output raises.
 
-Reference behaviours kept: CFG is active only when guidance_scale > 1 AND an unconditional embedding exists
-(:64-83); `scheduler.step` is ancestral DDPM (the reference passes no generator, :161) — here the per-step
+Reference behaviours kept: the unconditional embedding is prepended only when guidance_scale > 1 AND one exists
+(:64-83), while the latents are duplicated and the two halves combined whenever guidance_scale > 1 (:141,156-158;
+without an unconditional embedding MultiViewUNet repeats the text over both halves); `scheduler.step` is ancestral DDPM (the reference passes no generator, :161) — here the per-step
 variance noise comes from `generator` or from `variance_noises` (injected, for parity tests).
 """
 from __future__ import annotations
@@ -65,8 +66,9 @@ class MVDPipeline:
             raise NotImplementedError("pass negative_prompt_embeds instead of negative_prompt")
         dev = self.device
         batch_size = prompt_embeds.shape[0]
-        do_cfg = guidance_scale > 1.0 and negative_prompt_embeds is not None  # reference :64-83
-        if do_cfg:
+        do_cfg = guidance_scale > 1.0  # reference :141,156: duplication and combine depend on the scale alone
+        has_uncond = do_cfg and negative_prompt_embeds is not None  # reference :64-83
+        if has_uncond:
             prompt_embeds = torch.cat([negative_prompt_embeds.to(dev), prompt_embeds.to(dev)])
         height = height or self.unet.config.sample_size * self.vae_scale_factor
         width = width or self.unet.config.sample_size * self.vae_scale_factor
@@ -79,15 +81,17 @@ class MVDPipeline:
                 source_image_latents = source_image_latents.repeat(batch_size // source_image_latents.shape[0], 1, 1, 1)
 
         if use_cuda_graph:  # whole loop on the device: one captured step replayed num_inference_steps times
-            sess = DenoiseSession(self, prompt_embeds[batch_size:] if do_cfg else prompt_embeds, num_inference_steps,
-                                  guidance_scale, prompt_embeds[:batch_size] if do_cfg else None, source_camera,
-                                  target_camera, source_image_latents, latent_size=latents.shape[-1])
+            sess = DenoiseSession(self, prompt_embeds[batch_size:] if has_uncond else prompt_embeds,
+                                  num_inference_steps, guidance_scale,
+                                  prompt_embeds[:batch_size] if has_uncond else None, source_camera, target_camera,
+                                  source_image_latents, latent_size=tuple(latents.shape[-2:]))
             if variance_noises is None:
                 variance_noises = torch.randn((sess.n_steps,) + tuple(latents.shape), device=dev, dtype=torch.float32,
                                               generator=generator)
             sess.reset(latents, variance_noises)
             latents = sess.run().clone()
             self.gpu_launch_count += sess.launches_per_step * sess.n_steps
+            sess.close()
             return latents if not return_dict else {"images": latents, "latents": latents}
 
         self.scheduler.set_timesteps(num_inference_steps)
@@ -126,18 +130,25 @@ class DenoiseSession:
 
     Per-step scalars (timestep, DDPM coefficients) and the per-step variance noise are read on the device from
     tables indexed by a device-side counter. The reference draws its positional projection on every UNet call;
-    a session pins ONE draw for its lifetime (required for replay; pass `pos_proj` to choose it)."""
+    a session pins ONE draw for its lifetime (required for replay; pass `pos_proj` to choose it) and `close()`
+    (also the context-manager exit) puts the encoder back to per-call draws if the session was the one that pinned it.
+    `latent_size` is the latent height/width: an int (square) or an (H, W) pair.
+
+    A captured step holds the addresses of every step-invariant tensor it read (weight packs, reference K/V, text
+    K/V, camera embedding). Those caches are keyed on (data_ptr, _version), so a new source image, new cameras or
+    reloaded weights must arrive as NEW tensors or through torch ops — and then `invalidate()` must be called so
+    that the next step re-captures instead of replaying stale addresses."""
 
     def __init__(self, pipe: "MVDPipeline", prompt_embeds: torch.Tensor, num_inference_steps: int,
                  guidance_scale: float = 1.0, negative_prompt_embeds: Optional[torch.Tensor] = None,
                  source_camera: Optional[torch.Tensor] = None, target_camera: Optional[torch.Tensor] = None,
-                 source_image_latents: Optional[torch.Tensor] = None, latent_size: int = 64,
+                 source_image_latents: Optional[torch.Tensor] = None, latent_size=64,
                  use_cuda_graph: bool = True, pos_proj: Optional[torch.Tensor] = None, with_noise: bool = True):
         self.pipe, self.unet, dev = pipe, pipe.unet, pipe.device
-        self.cfg = 2 if (guidance_scale > 1.0 and negative_prompt_embeds is not None) else 1
+        self.cfg = 2 if guidance_scale > 1.0 else 1  # reference pipeline.py:141,156
         self.guidance = float(guidance_scale)
         text = prompt_embeds.to(dev)
-        if self.cfg == 2:
+        if self.cfg == 2 and negative_prompt_embeds is not None:  # reference :79-81
             text = torch.cat([negative_prompt_embeds.to(dev), text])
         self.text = text.contiguous()
         self.views = prompt_embeds.shape[0]
@@ -149,8 +160,11 @@ class DenoiseSession:
         if source_image_latents is not None:
             self.extra["source_image_latents"] = source_image_latents.to(dev).contiguous()
         cam = getattr(self.unet, "camera_encoder", None)
+        self._unpin = None
         if cam is not None and target_camera is not None and (pos_proj is not None or cam._pos_proj is None):
+            previous = cam._pos_proj
             cam.set_positional_projection(pos_proj if pos_proj is not None else cam._projection(dev).float())
+            self._unpin = (cam, cam._pos_proj, previous)
         sched = pipe.scheduler
         sched.set_timesteps(num_inference_steps)
         self.timesteps = [int(t) for t in sched.timesteps]
@@ -160,7 +174,8 @@ class DenoiseSession:
             coef[i, 0] = float(t)
             coef[i, 1:6] = torch.tensor(sched.coefficients(t))
         self.coef = coef.to(dev)
-        self.latents = torch.zeros(self.views, 4, latent_size, latent_size, device=dev, dtype=torch.float32)
+        lat_h, lat_w = (latent_size, latent_size) if isinstance(latent_size, int) else tuple(latent_size)
+        self.latents = torch.zeros(self.views, 4, lat_h, lat_w, device=dev, dtype=torch.float32)
         self.noise_table = torch.zeros(self.n_steps, self.latents.numel(), device=dev, dtype=torch.float32) \
             if with_noise else None
         self.step_idx = torch.zeros(1, device=dev, dtype=torch.int32)
@@ -182,6 +197,28 @@ class DenoiseSession:
         self.graph = None
         self.use_cuda_graph = use_cuda_graph
         self.launches_per_step = 0
+
+    def invalidate(self):
+        """Forget the captured step: the next `step()` warms the caches again and re-records. Call after anything the
+        step treats as invariant was replaced (weights, source-image latents, cameras, text)."""
+        self.graph = None
+
+    def close(self):
+        """Release the graph and, if this session pinned the camera encoder's positional projection, restore what was
+        there before (None = the reference's per-call draws) — unless someone re-pinned it since."""
+        self.graph = None
+        if self._unpin is not None:
+            cam, mine, previous = self._unpin
+            if cam._pos_proj is mine:
+                cam.set_positional_projection(previous)
+            self._unpin = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     def reset(self, latents: torch.Tensor, variance_noises: Optional[torch.Tensor] = None):
         """Load initial latents (and per-step noise [steps, V,4,L,L]); rewinds the step counter."""

@@ -177,3 +177,39 @@ def test_load_base_weights_reseeds_adapters_and_string_path_warns(tmp_path):
         warnings.simplefilter("error")
         cfg_path_model = mvd_b200.mvd_unet._find_unet_weights(str(tmp_path))
     assert cfg_path_model is not None and cfg_path_model.endswith(".safetensors")
+
+
+def test_session_cfg_gating_pin_restore_and_cache_invalidation():
+    """the CFG halves exist whenever guidance_scale > 1 (reference pipeline.py:141,156), with or
+    without an unconditional embedding; a session that pinned the positional projection puts the encoder back on
+    close(); rectangular latents; invalidate_caches() empties every private cache."""
+    m = mvd_b200.MultiViewUNet(tiny_config(), dtype=torch.float32)
+    pipe = mvd_b200.MVDPipeline(m, mvd_b200.DDPMScheduler())
+    text = torch.zeros(2, 77, tiny_config()["cross_attention_dim"])
+    cams = torch.eye(4)[None].repeat(2, 1, 1)
+    from mvd_b200.pipeline import DenoiseSession
+
+    assert m.camera_encoder._pos_proj is None
+    with DenoiseSession(pipe, text, 4, guidance_scale=3.0, negative_prompt_embeds=None, source_camera=cams,
+                        target_camera=cams, latent_size=(8, 16), use_cuda_graph=False, with_noise=False) as sess:
+        assert sess.cfg == 2 and sess.text.shape[0] == 2          # duplicated latents, text repeated by the UNet
+        assert tuple(sess.latents.shape) == (2, 4, 8, 16)
+        assert m.camera_encoder._pos_proj is not None
+    assert m.camera_encoder._pos_proj is None                       # restored: per-call draws as in the reference
+    sess = DenoiseSession(pipe, text, 4, guidance_scale=3.0, negative_prompt_embeds=text, latent_size=8,
+                          use_cuda_graph=False, with_noise=False)
+    assert sess.cfg == 2 and sess.text.shape[0] == 4
+    assert DenoiseSession(pipe, text, 4, guidance_scale=1.0, negative_prompt_embeds=text, latent_size=8,
+                          use_cuda_graph=False, with_noise=False).cfg == 1
+    # a pin the caller made is left alone
+    mine = torch.zeros(m.camera_encoder.output_dim, 6 * m.camera_encoder.pos_enc_dim)
+    m.camera_encoder.set_positional_projection(mine)
+    kept = m.camera_encoder._pos_proj
+    DenoiseSession(pipe, text, 4, source_camera=cams, target_camera=cams, latent_size=8, use_cuda_graph=False,
+                   with_noise=False).close()
+    assert m.camera_encoder._pos_proj is kept
+    m.camera_encoder.__dict__["_mod_cache"] = {"x": 1}
+    next(iter(m.attention_layer_map.values())).processor.__dict__["_ref_cache"] = ("k", "v", "r")
+    assert m.invalidate_caches() >= 2
+    assert "_mod_cache" not in m.camera_encoder.__dict__
+    assert m.invalidate_caches() == 0
