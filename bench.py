@@ -282,6 +282,67 @@ def cpu_baseline(reps=2, warmup=1, model=None):
             "sample_seconds": sec, "sample_fraction": SAMPLE_VIEWS / VIEWS}, timed
 
 
+def processor_c0(dev):
+    """configs[0] of BASELINE.json — the reference's own CPU-runnable case: ONE ImageCrossAttentionProcessor forward
+    (original self-attention + reference branch, attention.py:48-188) on hidden [4,4096,320], reference [4,320,64,64],
+    5 heads. CPU: the oracle's processor (checked to 0.0 max-abs against the live reference processor by
+    oracle/gen_golden.py), fp32, all host threads, 2 warm-ups, best of 5. GPU: the product's processor through the
+    same call (K/V cache warm, as in every step but the first), CUDA events, 3 warm-ups, mean of 20. Parity between
+    the two is printed."""
+    from helpers import metrics
+    from oracle import mv_adapter
+    from oracle.sd21_unet import Attention as OAttention
+
+    import mvd_b200
+    from mvd_b200 import unet as punet
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(11)
+    name, c, heads, views, side = "down_block_0_attn_0_self", 320, 5, 4, 64
+    torch.manual_seed(11)
+    attn_o = OAttention(c, heads, 64)
+    proc_o = mv_adapter.make_processor(name, attn_o, img_ref_scale=1.0)
+    with torch.no_grad():
+        for w in (proc_o.to_k_ref.weight, proc_o.to_v_ref.weight, proc_o.to_out_ref[0].weight):
+            w.add_(0.02 * torch.randn(w.shape, generator=g))
+    attn_o.processor = proc_o
+    hidden = torch.randn(views, side * side, c, generator=g)
+    ref = torch.randn(views, c, side, side, generator=g)
+    times = []
+    with torch.no_grad():
+        for _ in range(7):
+            t0 = time.time()
+            y_o = attn_o(hidden, ref_hidden_states={name: ref})
+            times.append(time.time() - t0)
+    cpu_ms = min(times[2:]) * 1e3
+    flops = views * (2 * 4 * side ** 4 * c + 8 * 2 * side * side * c * c)  # 2 SDPA + 8 projections per view
+    attn_p = punet.Attention(c, heads, 64)
+    attn_p.load_state_dict(attn_o.state_dict(), strict=False)
+    attn_p = attn_p.to(dev, torch.bfloat16)
+    proc_p = mvd_b200.get_attention_processor_for_module(name, attn_p, img_ref_scale=1.0)
+    proc_p.load_state_dict(proc_o.state_dict())
+    attn_p.processor = proc_p.to(dev, torch.bfloat16)
+    hs, rf = hidden.to(dev, torch.bfloat16), {name: ref.to(dev)}
+    with torch.no_grad():
+        for _ in range(3):
+            y_p = attn_p(hs, ref_hidden_states=rf)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            y_p = attn_p(hs, ref_hidden_states=rf)
+        e1.record()
+        torch.cuda.synchronize()
+    gpu_ms = e0.elapsed_time(e1) / 20
+    m = metrics(y_p.float().cpu(), y_o)
+    return {"workload": "configs[0]: one ImageCrossAttentionProcessor forward, hidden [4,4096,320], ref [4,320,64,64], "
+                        "5 heads", "cpu_ms": round(cpu_ms, 2), "cpu_tflops": round(flops / cpu_ms / 1e9, 3),
+            "cpu": "oracle processor (0.0 max-abs vs the live reference processor), fp32, best of 5",
+            "cores": torch.get_num_threads(), "gpu_ms": round(gpu_ms, 4),
+            "gpu": "product processor, bf16, eager launches (no graph), reference K/V cached, mean of 20",
+            "normalised_max_abs": round(m["rel"], 5), "cosine": round(m["cos"], 6)}
+
+
 def parity_check(pipe, sess_latents, dev):
     """The timed model against the oracle at a size the oracle finishes in seconds (2 views x 32^2, cfg 1), same
     weights; and sanity of what the timed configuration itself produced."""
@@ -520,6 +581,10 @@ def run_ours(args):
                 result["line"]["parity"] = {"error": f"{type(exc).__name__}: {exc}"[:300], "ok": False}
         if not args.no_cpu_baseline and args.workload == "c1":
             result["line"]["cpu_baseline"] = cpu_baseline()[0]
+            try:
+                result["line"]["cpu_baseline"]["c0"] = processor_c0(dev)
+            except Exception as exc:  # noqa: BLE001
+                result["line"]["cpu_baseline"]["c0"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
     finished.set()
     emit()
     # All measurements are done and reported. Skip the NCCL teardown on purpose: destroy_process_group() after a
