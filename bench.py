@@ -192,9 +192,11 @@ def attention_roofline(dev, pk, how):
         return sum(times) / len(times)
 
     ms = timed()  # a stand-alone launch: the last partial wave is split along S_kv over the idle SMs
-    # inside the step this site runs as two concurrent launches (self / reference branch on two streams) that fill each
-    # other's last wave, so neither splits (co_units): the same kernel, timed alone in that configuration
-    ms_in_step_cfg = timed(co_units=ops.attention_units(B, H, S))
+    # Inside the step: with persistent CTAs (default) the two branches of an adapter block follow each other on one
+    # stream, each launched exactly as above. Without (MVD_ATTN_PERSIST=0) they run concurrently on two streams and
+    # fill each other's last wave, so neither splits (co_units): the same kernel, timed alone in that configuration.
+    persistent = ops.ATTN_PERSIST and ops.attention_units(B, H, S) >= torch.cuda.get_device_properties(dev).multi_processor_count
+    ms_in_step_cfg = ms if persistent else timed(co_units=ops.attention_units(B, H, S))
     flops = 4.0 * S * s_kv * C * B
     achieved = flops / (ms * 1e-3) / 1e12
     peak = pk["bf16_tflops"]
@@ -204,14 +206,15 @@ def attention_roofline(dev, pk, how):
             traffic = json.load(open(os.path.join(ROOT, "profiles", "attn_traffic.json")))["dram_bytes_per_launch"]
         except Exception:
             pass
-    return {"kernel": f"attn_pair_kernel (B={B},h={H},Sq={S},Skv={s_kv},d=64)", "bound": "tensor", "achieved": round(achieved, 1),
+    return {"kernel": f"{'attn_pair_persist_kernel' if persistent else 'attn_pair_kernel'} (B={B},h={H},Sq={S},Skv={s_kv},d=64)", "bound": "tensor", "achieved": round(achieved, 1),
             "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4), "traffic": traffic,
             "peak_source": f"{how} burst bf16 GEMM", "ms_per_launch": round(ms, 4),
             "flops_per_launch": flops,
             "as_launched_in_step": {"ms_per_launch": round(ms_in_step_cfg, 4),
                                     "achieved": round(flops / (ms_in_step_cfg * 1e-3) / 1e12, 1),
                                     "frac": round(flops / (ms_in_step_cfg * 1e-3) / 1e12 / peak, 4),
-                                    "note": "no KV-split tail: the concurrent sibling launch fills the last wave"}}
+                                    "note": "persistent CTAs, launched as timed above" if persistent else
+                                            "no KV-split tail: the concurrent sibling launch fills the last wave"}}
 
 
 _ORACLE = None

@@ -210,6 +210,11 @@ int mvd_conv_in_f32_bf16(const float* latents, int n_latents, const float* mod, 
 int mvd_conv_out_bf16_f32(const void* x, const void* w, const void* bias, float* out, int n_img, int h, int wdt,
                           int c_in, void* stream);
 
+/* The first 4 channels of an NHWC bf16 tensor (pixel stride ld elements) as fp32 NCHW [n_img,4,hw]: the tail of the
+ * UNet's conv_out (diffusers unet_2d_condition.py conv_out; reference call site src/models/mvd_unet.py:318) when that
+ * conv runs through mvd_conv3x3_bf16 with its 4 weight rows zero-padded to 32. */
+int mvd_head4_to_nchw_f32(const void* x, int64_t ld, float* out, int n_img, int64_t hw, void* stream);
+
 /* F.interpolate(scale_factor=2, mode="nearest") of diffusers Upsample2D, NHWC bf16. */
 int mvd_upsample_nearest2x_bf16(const void* x, void* out, int n_img, int h, int wdt, int channels, void* stream);
 

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "mvd_conv_in_f32_bf16": (_I, [_P, _I, _P, _I, _F, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mvd_conv_out_bf16_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _P]),
     "mvd_upsample_nearest2x_bf16": (_I, [_P, _P, _I, _I, _I, _I, _P]),
+    "mvd_head4_to_nchw_f32": (_I, [_P, _L, _P, _I, _L, _P]),
     "mvd_add_bf16": (_I, [_P, _P, _P, _L, _P]),
     "mvd_cast_f32_bf16": (_I, [_P, _P, _L, _P]),
     "mvd_transpose_batched": (_I, [_P, _P, _I, _I, _I, _I, _I, _P]),

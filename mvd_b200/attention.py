@@ -251,7 +251,16 @@ class ImageCrossAttentionProcessor(nn.Module):
             # The two branches are independent until the fused out-projection. Each launch is a non-integral
             # number of one-CTA-per-SM waves, so the reference branch is forked onto a second stream to fill the
             # tail of the first (inside a captured step this becomes two parallel graph branches).
-            if OVERLAP_BRANCHES:
+            units = ops.attention_units(b, self.heads, s)
+            big = units >= _sm_count(hidden_states.device)
+            sms = _sm_count(hidden_states.device)
+            if not pk["is_cross"] and (ops.attention_is_persistent(b, self.heads, s, k.shape[1], sms) or
+                                       ops.attention_is_persistent(b, self.heads, s, k_ref.shape[1], sms)):
+                # each launch is a persistent grid of one CTA per SM that splits its own last wave along S_kv: nothing
+                # is left for a sibling to fill, so the two branches simply follow each other on this stream
+                ops.attention(q, k, v, self.heads, scale, out=cat[:, :, :c])
+                ops.attention(q_ref, k_ref, v_ref, self.heads, scale, out=cat[:, :, c:])
+            elif OVERLAP_BRANCHES:
                 main = torch.cuda.current_stream()
                 side = _branch_stream(hidden_states.device)
                 fork, join = torch.cuda.Event(), torch.cuda.Event()
@@ -261,8 +270,6 @@ class ImageCrossAttentionProcessor(nn.Module):
                 # the main one splits, and only its share of the COMBINED last wave (co_units). Small launches (a
                 # view-sharded rank: fewer units than SMs) both split. Next to the tiny text attention the reference
                 # branch simply owns the machine.
-                units = ops.attention_units(b, self.heads, s)
-                big = units >= _sm_count(hidden_states.device)
                 if pk["is_cross"]:
                     side_kw, main_kw = dict(split_tail=True), dict(split_tail=False)
                 elif big:

@@ -741,6 +741,437 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
   }
 }
 
+
+// ================================================================================================
+// Persistent form of attn_pair_kernel for launches of at least one wave of units: one CTA per SM walks the work items
+// (whole units first, then the KV parts of the split tail) round-robin. What it buys over one CTA per item: barrier
+// initialisation, TMEM allocation and descriptor prefetch happen once per SM; Q of the next item is prefetched into a
+// second shared-memory buffer and K/V keep streaming through the ring across the item boundary; the MMA warp issues
+// QK(0) of the next item in the slot where QK(j+1) would go, so S is already waiting when the softmax warps come back
+// from the epilogue, whose global stores then overlap the next item's first blocks. All barriers run on global
+// counters (g: KV blocks of this CTA so far, it: items so far) instead of per-item ones; two more barriers order the
+// item boundary: q_empty (all QK of an item retired -> its Q buffer may be refilled) and o_free (the epilogue has
+// read O_t from TMEM -> PV_t(0) of the next item may overwrite it).
+// ================================================================================================
+constexpr int ATT3_SMEM = (4 + 2 * ATT2_KS) * ATT_TILE_BYTES + 1024 + 1024;
+constexpr int ATT_PERSIST_MAX_BLOCKS = 96;  // KV blocks per item up to which the persistent form is used
+
+struct PairItem {
+  int unit, part, nparts, q_pair, head, batch, kb0, n_blocks;
+};
+__device__ __forceinline__ PairItem pair_item(const PairSched& sc, int skv, int idx) {
+  PairItem w;
+  w.unit = idx;
+  w.part = 0;
+  w.nparts = 1;
+  if (idx >= sc.n_full) {
+    const int r = idx - sc.n_full;
+    w.unit = sc.n_full + r / sc.split;
+    w.part = r % sc.split;
+    w.nparts = sc.split;
+  }
+  w.q_pair = w.unit % sc.q_pairs;
+  w.head = (w.unit / sc.q_pairs) % sc.heads;
+  w.batch = w.unit / (sc.q_pairs * sc.heads);
+  const int n_all = (skv + ATT_BN - 1) / ATT_BN;
+  w.kb0 = n_all * w.part / w.nparts;
+  w.n_blocks = n_all * (w.part + 1) / w.nparts - w.kb0;
+  return w;
+}
+
+template <int POLY8>
+__global__ void __launch_bounds__(ATT2_THREADS, 1)
+attn_pair_persist_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
+                         const __grid_constant__ CUtensorMap mapV, const AttnArgs p, const PairSched sc,
+                         const int n_items) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;  // two buffers of two tiles
+  uint8_t* sK = smem + 4 * ATT_TILE_BYTES;
+  uint8_t* sV = sK + ATT2_KS * ATT_TILE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT2_KS * ATT_TILE_BYTES);
+  uint64_t* q_full = bars;                   // [2] per Q buffer
+  uint64_t* q_empty = bars + 2;              // [2]
+  uint64_t* k_full = bars + 4;               // [KS]
+  uint64_t* k_empty = k_full + ATT2_KS;      // [KS]
+  uint64_t* v_full = k_empty + ATT2_KS;      // [KS]
+  uint64_t* v_empty = v_full + ATT2_KS;      // [KS]
+  uint64_t* s_full = v_empty + ATT2_KS;      // [2] per tile
+  uint64_t* p_full = s_full + 2;             // [2]
+  uint64_t* s_free = p_full + 2;             // [2]
+  uint64_t* pv_done = s_free + 2;            // [2]
+  uint64_t* o_free = pv_done + 2;            // [2]
+  uint64_t* o_final = o_free + 2;            // [2] per tile: the two warpgroups must NOT meet at the item boundary
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_final + 2);
+  uint32_t* last_flag = tmem_slot + 1;
+
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+  const int lane = threadIdx.x & 31;
+  const int n_ctas = gridDim.x;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&mapQ);
+    tma_prefetch_desc(&mapK);
+    tma_prefetch_desc(&mapV);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&q_full[b], 1);
+      mbar_init(&q_empty[b], 1);
+    }
+    for (int s = 0; s < ATT2_KS; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&p_full[t], 4);
+      mbar_init(&s_free[t], 4);
+      mbar_init(&pv_done[t], 1);
+      mbar_init(&o_free[t], 4);
+      mbar_init(&o_final[t], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == 0) {
+      // ===================== TMA producer =====================
+      if (lane == 0) {
+        uint32_t g = 0;
+        int it = 0;
+        for (int idx = blockIdx.x; idx < n_items; idx += n_ctas, ++it) {
+          const PairItem w = pair_item(sc, p.Skv, idx);
+          const int qb = it & 1;
+          mbar_wait(&q_empty[qb], ((it >> 1) & 1) ^ 1);
+          uint8_t* q_dst = sQ + qb * 2 * ATT_TILE_BYTES;
+          mbar_arrive_expect_tx(&q_full[qb], 2 * ATT_TILE_BYTES);
+          tma_load_3d(q_dst, &mapQ, &q_full[qb], w.head * ATT_D, w.q_pair * 256, w.batch);
+          tma_load_3d(q_dst + ATT_TILE_BYTES, &mapQ, &q_full[qb], w.head * ATT_D, w.q_pair * 256 + 128, w.batch);
+          for (int j = 0; j < w.n_blocks; ++j, ++g) {
+            const int s = g % ATT2_KS;
+            const uint32_t ph = (g / ATT2_KS) & 1;
+            mbar_wait(&k_empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&k_full[s], ATT_TILE_BYTES);
+            tma_load_3d(sK + s * ATT_TILE_BYTES, &mapK, &k_full[s], w.head * ATT_D, (w.kb0 + j) * ATT_BN,
+                        w.batch * p.kv_batch_mul);
+            mbar_wait(&v_empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&v_full[s], ATT_TILE_BYTES);
+            tma_load_3d(sV + s * ATT_TILE_BYTES, &mapV, &v_full[s], w.head * ATT_D, (w.kb0 + j) * ATT_BN,
+                        w.batch * p.kv_batch_mul);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      // ===================== MMA issuer =====================
+      constexpr uint32_t idesc_qk = umma_idesc_bf16(ATT_BM, ATT_BN, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(ATT_BM, ATT_D, false, /*b_mn_major=*/true);
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t q_addr = __shfl_sync(0xffffffffu, smem_u32(sQ), 0);
+      const uint32_t k_addr = __shfl_sync(0xffffffffu, smem_u32(sK), 0);
+      const uint32_t v_addr = __shfl_sync(0xffffffffu, smem_u32(sV), 0);
+      auto issue_qk = [&](int t, int qb, int slot, bool release_k) {  // S_t = Q_t K^T
+        const uint64_t qdesc = umma_desc_sw128(q_addr + (qb * 2 + t) * ATT_TILE_BYTES);
+        const uint64_t kdesc = umma_desc_sw128(k_addr + slot * ATT_TILE_BYTES);
+        const uint32_t d = tb + tm2_s(t);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < ATT_D / 16; ++k) umma_ss(d, qdesc + 2 * k, kdesc + 2 * k, idesc_qk, k != 0);
+          umma_commit(&s_full[t]);
+          if (release_k) umma_commit(&k_empty[slot]);
+        }
+        __syncwarp();
+      };
+      auto issue_pv = [&](int t, int slot, bool accumulate, bool release_v) {  // O_t (+)= P_t V
+        const uint64_t vdesc = umma_desc_sw128(v_addr + slot * ATT_TILE_BYTES);
+        const uint32_t a_tmem = tb + tm2_p(t);
+        const uint32_t d = tb + tm2_o(t);
+        if (elect_one()) {
+          umma_ts(d, a_tmem, vdesc, idesc_pv, accumulate);
+#pragma unroll
+          for (int k = 1; k < ATT_BN / 16; ++k) umma_ts(d, a_tmem + 8 * k, vdesc + 128 * k, idesc_pv, 1);
+          umma_commit(&pv_done[t]);
+          if (release_v) umma_commit(&v_empty[slot]);
+        }
+        __syncwarp();
+      };
+      int idx = blockIdx.x;
+      if (idx < n_items) {
+        PairItem w = pair_item(sc, p.Skv, idx);
+        uint32_t g = 0;
+        int it = 0;
+        mbar_wait(&q_full[0], 0);
+        mbar_wait(&k_full[0], 0);
+        tc_fence_after();
+        issue_qk(0, 0, 0, false);
+        issue_qk(1, 0, 0, true);
+        while (true) {
+          const bool has_next = idx + n_ctas < n_items;
+          for (int j = 0; j < w.n_blocks; ++j, ++g) {
+            const uint32_t par = g & 1;
+            const bool more = j + 1 < w.n_blocks;
+            const bool next_qk = more || has_next;  // the block after this one: same item, or block 0 of the next
+            const uint32_t ng = g + 1;
+            const int nslot = ng % ATT2_KS;
+            const int nqb = more ? (it & 1) : ((it + 1) & 1);
+            if (next_qk) {
+              if (!more) mbar_wait(&q_full[nqb], ((it + 1) >> 1) & 1);
+              mbar_wait(&k_full[nslot], (ng / ATT2_KS) & 1);
+              mbar_wait(&s_free[0], par);
+              tc_fence_after();
+              issue_qk(0, nqb, nslot, false);
+            }
+            if (j > 0) {
+              mbar_wait(&p_full[1], par ^ 1);
+              if (j == 1 && it > 0) mbar_wait(&o_free[1], (it - 1) & 1);
+              tc_fence_after();
+              issue_pv(1, (g - 1) % ATT2_KS, j != 1, true);
+            }
+            if (next_qk) {
+              mbar_wait(&s_free[1], par);
+              tc_fence_after();
+              issue_qk(1, nqb, nslot, true);
+            }
+            mbar_wait(&v_full[g % ATT2_KS], (g / ATT2_KS) & 1);
+            mbar_wait(&p_full[0], par);
+            if (j == 0 && it > 0) mbar_wait(&o_free[0], (it - 1) & 1);
+            tc_fence_after();
+            issue_pv(0, g % ATT2_KS, j != 0, false);
+            // O_A is final half a block before O_B: tile A's warpgroup goes through its epilogue and into the next
+            // item while tile B still exponentiates, so the anti-phase of the two survives the item boundary
+            if (!more) {
+              if (elect_one()) umma_commit(&o_final[0]);
+              __syncwarp();
+            }
+          }
+          mbar_wait(&p_full[1], (g - 1) & 1);
+          if (w.n_blocks == 1 && it > 0) mbar_wait(&o_free[1], (it - 1) & 1);
+          tc_fence_after();
+          issue_pv(1, (g - 1) % ATT2_KS, w.n_blocks != 1, true);
+          if (elect_one()) {
+            umma_commit(&o_final[1]);
+            umma_commit(&q_empty[it & 1]);
+          }
+          __syncwarp();
+          if (!has_next) break;
+          idx += n_ctas;
+          w = pair_item(sc, p.Skv, idx);
+          ++it;
+        }
+      }
+    }
+  } else {
+    // ===================== softmax warpgroups (warps 4..7: tile A, 8..11: tile B) =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 224;");
+    const int t = (warp - 4) >> 2;
+    const int q = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(q * 32) << 16;
+    const int row_in_tile = q * 32 + lane;
+    const uint32_t t_s = tmem_base + tm2_s(t) + lane_off;
+    const uint32_t t_p = tmem_base + tm2_p(t) + lane_off;
+    const uint32_t t_o = tmem_base + tm2_o(t) + lane_off;
+    uint32_t g = 0;
+    int it = 0;
+    for (int idx = blockIdx.x; idx < n_items; idx += n_ctas, ++it) {
+      const PairItem w = pair_item(sc, p.Skv, idx);
+      float m_ref = -INFINITY;
+      float l = 0.f;
+      for (int j = 0; j < w.n_blocks; ++j, ++g) {
+        mbar_wait(&s_full[t], g & 1);
+        tc_fence_after();
+        float x[ATT_BN];
+        {
+          uint32_t* xr = reinterpret_cast<uint32_t*>(x);
+          tmem_ld_32x32b_x32(t_s + 0, xr + 0);
+          tmem_ld_32x32b_x32(t_s + 32, xr + 32);
+          tmem_ld_32x32b_x32(t_s + 64, xr + 64);
+          tmem_ld_32x32b_x32(t_s + 96, xr + 96);
+          // the wait for PV_t(j-1) sits before S_t is handed back on purpose (anti-phase of the two warpgroups; see
+          // attn_pair_kernel)
+          if (j > 0) mbar_wait(&pv_done[t], (g - 1) & 1);
+          tmem_ld_wait();
+          tc_fence_after();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[t]);
+        const int valid = p.Skv - (w.kb0 + j) * ATT_BN;
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+        if (valid >= ATT_BN) {
+          float mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < ATT_BN; c += 8) {
+            mx0 = max3f(mx0, x[c], x[c + 1]);
+            mx1 = max3f(mx1, x[c + 2], x[c + 3]);
+            mx2 = max3f(mx2, x[c + 4], x[c + 5]);
+            mx3 = max3f(mx3, x[c + 6], x[c + 7]);
+          }
+          mx0 = fmaxf(mx0, mx2);
+          mx1 = fmaxf(mx1, mx3);
+        } else {
+#pragma unroll
+          for (int c = 0; c < ATT_BN; ++c) {
+            x[c] = (c < valid) ? x[c] : -INFINITY;
+            mx0 = fmaxf(mx0, x[c]);
+          }
+        }
+        const float mx = fmaxf(mx0, mx1) * p.scale_log2;
+        const bool need = mx > m_ref + LAZY_RESCALE_THRESHOLD;
+        float alpha = 1.f;
+        if (need) {
+          alpha = ex2_approx(m_ref - mx);
+          m_ref = mx;
+        }
+        const float2 neg_m2 = make_float2(-m_ref, -m_ref);
+        const float2 scale2 = make_float2(p.scale_log2, p.scale_log2);
+        float2* x2 = reinterpret_cast<float2*>(x);
+        if (j > 0) {
+          if (__any_sync(0xffffffffu, need)) {
+#pragma unroll 1
+            for (int c0 = 0; c0 < ATT_D; c0 += 8) {
+              uint32_t o[8];
+              tmem_ld_32x32b_x8(t_o + c0, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int c = 0; c < 8; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tmem_st_32x32b_x8(t_o + c0, o);
+            }
+          }
+        }
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; i += 2) {
+            const int i0 = ch * 16 + i;
+            const float2 a0 = ffma2(x2[i0], scale2, neg_m2), a1 = ffma2(x2[i0 + 1], scale2, neg_m2);
+            float2 e0, e1;
+            if ((i0 & 7) < POLY8) e0 = ex2_poly2(a0);
+            else e0 = make_float2(ex2_approx(a0.x), ex2_approx(a0.y));
+            if (((i0 + 1) & 7) < POLY8) e1 = ex2_poly2(a1);
+            else e1 = make_float2(ex2_approx(a1.x), ex2_approx(a1.y));
+            acc0 = fadd2(acc0, e0);
+            acc1 = fadd2(acc1, e1);
+            pk[i] = pack_bf16x2(e0.x, e0.y);
+            pk[i + 1] = pack_bf16x2(e1.x, e1.y);
+          }
+          tmem_st_32x32b_x16(t_p + ch * 16, pk);
+        }
+        l = l * alpha + ((acc0.x + acc0.y) + (acc1.x + acc1.y));
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+
+      // ---- epilogue of the item
+      mbar_wait(&o_final[t], it & 1);
+      tc_fence_after();
+      float o[ATT_D];
+      {
+        uint32_t* orr = reinterpret_cast<uint32_t*>(o);
+        tmem_ld_32x32b_x32(t_o, orr);
+        tmem_ld_32x32b_x32(t_o + 32, orr + 32);
+        tmem_ld_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);  // PV_t(0) of the next item may overwrite O_t
+      const int row_in_unit = t * 128 + row_in_tile;
+      bool store = true;
+      if (w.nparts > 1) {
+        const int su = w.unit - sc.n_full;
+        const size_t slot = static_cast<size_t>(su) * w.nparts + w.part;
+        float4* wo = reinterpret_cast<float4*>(sc.ws_o) + slot * (16 * 256) + row_in_unit;
+#pragma unroll
+        for (int c = 0; c < ATT_D / 4; ++c) wo[c * 256] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+        reinterpret_cast<float2*>(sc.ws_ml)[slot * 256 + row_in_unit] = make_float2(m_ref, l);
+        __threadfence();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 128) {
+          const unsigned int old = atomicAdd(sc.ws_cnt + su, 1u);
+          const bool last = old == static_cast<unsigned int>(w.nparts - 1);
+          if (last) sc.ws_cnt[su] = 0u;
+          *last_flag = last ? 1u : 0u;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        store = *last_flag != 0u;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // everyone has read the flag before the next item rewrites it
+        if (store) {
+          __threadfence();
+          const size_t slot0 = static_cast<size_t>(su) * w.nparts;
+          const float2* mlp = reinterpret_cast<const float2*>(sc.ws_ml) + slot0 * 256 + row_in_unit;
+          float2 ml[ATT_MAX_SPLIT];
+          float m = -INFINITY;
+#pragma unroll
+          for (int pp = 0; pp < ATT_MAX_SPLIT; ++pp) {
+            if (pp < w.nparts) {
+              ml[pp] = __ldcg(mlp + pp * 256);
+              m = fmaxf(m, ml[pp].x);
+            }
+          }
+          l = 0.f;
+#pragma unroll
+          for (int c = 0; c < ATT_D; ++c) o[c] = 0.f;
+#pragma unroll 1
+          for (int pp = 0; pp < w.nparts; ++pp) {
+            float wgt = 0.f;
+#pragma unroll
+            for (int k = 0; k < ATT_MAX_SPLIT; ++k)
+              if (k == pp) wgt = ex2_approx(ml[k].x - m), l = fmaf(wgt, ml[k].y, l);
+            const float4* src = reinterpret_cast<const float4*>(sc.ws_o) + (slot0 + pp) * (16 * 256) + row_in_unit;
+            float4 f[ATT_D / 4];
+#pragma unroll
+            for (int c = 0; c < ATT_D / 4; ++c) f[c] = __ldcg(src + c * 256);
+#pragma unroll
+            for (int c = 0; c < ATT_D / 4; ++c) {
+              o[4 * c] = fmaf(wgt, f[c].x, o[4 * c]);
+              o[4 * c + 1] = fmaf(wgt, f[c].y, o[4 * c + 1]);
+              o[4 * c + 2] = fmaf(wgt, f[c].z, o[4 * c + 2]);
+              o[4 * c + 3] = fmaf(wgt, f[c].w, o[4 * c + 3]);
+            }
+          }
+        }
+      }
+      const int row = w.q_pair * 256 + row_in_unit;
+      if (store && row < p.Sq) {
+        const float inv_l = 1.f / l;
+        __nv_bfloat16* dst = p.out + static_cast<int64_t>(w.batch) * p.o_batch_stride +
+                             static_cast<int64_t>(row) * p.ldo + w.head * ATT_D;
+#pragma unroll
+        for (int c = 0; c < ATT_D; c += 8) {
+          uint4 v;
+          v.x = pack_bf16x2(o[c + 0] * inv_l, o[c + 1] * inv_l);
+          v.y = pack_bf16x2(o[c + 2] * inv_l, o[c + 3] * inv_l);
+          v.z = pack_bf16x2(o[c + 4] * inv_l, o[c + 5] * inv_l);
+          v.w = pack_bf16x2(o[c + 6] * inv_l, o[c + 7] * inv_l);
+          *reinterpret_cast<uint4*>(dst + c) = v;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TM_COLS);
+  }
+}
+
 }  // namespace mvd
 
 namespace {
@@ -861,6 +1292,31 @@ extern "C" int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch
       const char* e = getenv("MVD_ATTN_POLY8");
       return e ? atoi(e) : 0;
     }();
+    // at least one whole wave of units: persistent CTAs (one per SM) walk the items
+    static const bool persist_on = [] {
+      const char* e = getenv("MVD_ATTN_PERSIST");
+      return e == nullptr || e[0] != '0';
+    }();
+    // (long items amortise the per-item costs by themselves, and measured slower in this form: configs[3]'s 576-block
+    // reference attention 2.20 vs 2.09 ms, step 125.5 vs 122.1 ms)
+    if (persist_on && !trace && units >= sms && n_blocks <= ATT_PERSIST_MAX_BLOCKS) {
+      const int n_items = static_cast<int>(grid.x);
+      const dim3 pgrid(n_items < sms ? n_items : sms);
+#define MVD_PAIR_P(POLY)                                                                                                \
+  do {                                                                                                                  \
+    MVD_CUDA(cudaFuncSetAttribute(attn_pair_persist_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
+                                  ATT3_SMEM));                                                                          \
+    MVD_CUDA(launch_pdl(attn_pair_persist_kernel<POLY>, pgrid, dim3(ATT2_THREADS), ATT3_SMEM, st, mQ, mK, mV, a, sc,    \
+                        n_items));                                                                                      \
+  } while (0)
+      if (poly == 1) MVD_PAIR_P(1);
+      else if (poly == 2) MVD_PAIR_P(2);
+      else MVD_PAIR_P(0);
+#undef MVD_PAIR_P
+      MVD_CUDA(cudaGetLastError());
+      count_launches(1);
+      return MVD_OK;
+    }
 #define MVD_PAIR(POLY, TR)                                                                                              \
   do {                                                                                                                  \
     MVD_CUDA(cudaFuncSetAttribute(attn_pair_kernel<POLY, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM)); \

@@ -359,6 +359,23 @@ upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ out, int N, i
   out[i] = x[((static_cast<int64_t>(n) * H + (yo >> 1)) * W + (xo >> 1)) * cvec + c];
 }
 
+// First 4 channels of an NHWC bf16 tensor (row stride ld elements) -> fp32 NCHW [N,4,HW]: the tail of conv_out when it
+// runs as a 32-column tcgen05 conv (zero-padded weight rows). Thread per pixel: one 8-byte load, four coalesced stores.
+__global__ void __launch_bounds__(256)
+head4_to_nchw_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t ld, float* __restrict__ out, int N, int64_t HW) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<int64_t>(N) * HW) return;
+  const int64_t n = i / HW, px = i - n * HW;
+  const uint2 v = *reinterpret_cast<const uint2*>(x + i * ld);
+  float* o = out + n * 4 * HW + px;
+  o[0] = __uint_as_float(v.x << 16);
+  o[HW] = __uint_as_float(v.x & 0xffff0000u);
+  o[2 * HW] = __uint_as_float(v.y << 16);
+  o[3 * HW] = __uint_as_float(v.y & 0xffff0000u);
+}
+
 __global__ void __launch_bounds__(256)
 add_kernel(const uint4* __restrict__ a, const uint4* __restrict__ b, uint4* __restrict__ out, int64_t nvec) {
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -592,6 +609,18 @@ int mvd_upsample_nearest2x_bf16(const void* x, void* out, int n_img, int h, int 
   MVD_CUDA(launch_pdl(upsample2x_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
                       static_cast<cudaStream_t>(stream), static_cast<const uint4*>(x), static_cast<uint4*>(out), n_img, h,
                       wdt, channels / 8));
+  MVD_CUDA(cudaGetLastError());
+  count_launches(1);
+  return MVD_OK;
+}
+
+int mvd_head4_to_nchw_f32(const void* x, int64_t ld, float* out, int n_img, int64_t hw, void* stream) {
+  using namespace mvd;
+  MVD_CHECK(n_img > 0 && hw > 0 && ld >= 4 && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0,
+            "head4_to_nchw: rows must be 8-byte aligned with a stride multiple of 4 elements");
+  const int64_t total = static_cast<int64_t>(n_img) * hw;
+  MVD_CUDA(launch_pdl(head4_to_nchw_f32_kernel, dim3(static_cast<unsigned>((total + 255) / 256)), dim3(256), 0,
+                      static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), ld, out, n_img, hw));
   MVD_CUDA(cudaGetLastError());
   count_launches(1);
   return MVD_OK;

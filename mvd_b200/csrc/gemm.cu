@@ -65,10 +65,63 @@ struct GemmArgs {
   const float* film_scale;
   const float* film_shift;
   int film_ld;
-  // split-K (SPLIT kernels): tiles_total counts (tile, k-slice) work items, slice fastest
-  int splits;                // k-slices per output tile
-  float4* ws_partial;        // [tile][slice][BN/4][128 rows] fp32 partial accumulators (lane = row: coalesced)
-  unsigned int* ws_tickets;  // [tile][4] arrival counters, one per 32-row warp slab; zero between launches
+  // stream-K (SPLIT kernels): tiles [0, sk_first) are whole-tile work items; the k-blocks of the remaining tiles — the
+  // last, partial wave, or all tiles of a launch smaller than the machine — are shared evenly by CTAs [0, sk_ctas)
+  int sk_first;
+  int sk_ctas;
+  int sk_units;              // (tiles_total - sk_first) * k_blocks
+  int sk_slots;              // partial-tile slots per stream-K tile (>= the CTAs that can touch one tile)
+  float4* ws_partial;        // [tile - sk_first][slot][BN/4][128 rows] fp32 partial accumulators (lane = row: coalesced)
+  unsigned int* ws_tickets;  // [tile - sk_first][4] arrival counters, one per 32-row warp slab; zero between launches
+};
+
+// One unit of a CTA's work: k-blocks [kb0, kb1) of an output tile. nsl == 1: the whole tile (normal epilogue);
+// nsl > 1: segment `slice` (in k order) of the nsl segments that different CTAs contribute to the tile.
+struct WorkItem {
+  int tile, kb0, kb1, slice, nsl;
+};
+
+// The sequence of work items of CTA `unit`, identical in the producer, MMA and epilogue roles. Stream-K segments come
+// first (their partial exchange then overlaps the whole-tile work of the other CTAs), whole tiles round-robin after.
+// CTA i of the stream-K set owns units [floor(i T / G), floor((i + 1) T / G)) of the T = tiles * k_blocks k-block units;
+// the CTA that owns unit u is floor(((u + 1) G - 1) / T)  (host guarantees T >= G and T * G < 2^31).
+template <bool SPLIT>
+struct WorkIter {
+  int u0, u1, t, step, n_direct, k_blocks, unit;
+  __device__ __forceinline__ WorkIter(const GemmArgs& p, int k_blocks_, int unit_, int n_units)
+      : u0(0), u1(0), t(unit_), step(n_units), n_direct(SPLIT ? p.sk_first : p.tiles_total), k_blocks(k_blocks_),
+        unit(unit_) {
+    if (SPLIT && unit_ < p.sk_ctas) {
+      u0 = unit_ * p.sk_units / p.sk_ctas;
+      u1 = (unit_ + 1) * p.sk_units / p.sk_ctas;
+    }
+  }
+  __device__ __forceinline__ bool next(const GemmArgs& p, WorkItem& w) {
+    if (SPLIT && u0 < u1) {
+      const int rel = u0 / k_blocks;
+      const int base = rel * k_blocks;
+      w.tile = p.sk_first + rel;
+      w.kb0 = u0 - base;
+      const int len = min(k_blocks - w.kb0, u1 - u0);
+      w.kb1 = w.kb0 + len;
+      const int c_first = ((base + 1) * p.sk_ctas - 1) / p.sk_units;
+      const int c_last = ((base + k_blocks) * p.sk_ctas - 1) / p.sk_units;
+      w.slice = unit - c_first;
+      w.nsl = c_last - c_first + 1;
+      u0 += len;
+      return true;
+    }
+    if (t < n_direct) {
+      w.tile = t;
+      w.kb0 = 0;
+      w.kb1 = k_blocks;
+      w.slice = 0;
+      w.nsl = 1;
+      t += step;
+      return true;
+    }
+    return false;
+  }
 };
 
 constexpr int WS_MAX_KBLOCKS = 5;  // weight-stationary tiles: K <= 320
@@ -110,12 +163,14 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 // Round 2 measured and removed CTA-pair tiles (cta_group::2, 256 x BN; 5-20 % slower at every M = 32768 linear, step
 // 13.74 vs 13.26 ms; profiles/r2_gemm_variants.txt).
-// SPLIT: split-K for launches that fill a fraction of the machine with LONG k-loops — the 16x16 and 8x8 levels of a
-// view-sharded rank (1-2 samples: 20-40 tiles, 180-360 k-blocks each, 25-39 us on 20-40 SMs). Each work item is a
-// (tile, k-slice); every CTA writes its fp32 partial tile to a workspace (column-chunk major, so a warp's 32 rows are
-// contiguous), and per 32-row slab the LAST arriving warp (ticket counter, re-armed for the next launch) adds the
-// slices in slice order — deterministic — and runs the normal epilogue on the sum. Round 1's version of this (row-
-// major partials, used at M = 512 where the k-loops are short) measured slower and is what round 2 removed.
+// SPLIT: stream-K for the part of a launch that does not fill the machine — all tiles of the 16x16 / 8x8 levels and of
+// a view-sharded rank (1-2 samples: 20-120 tiles with 45-360 k-blocks each), and the last partial wave of the big
+// launches. The k-blocks of those tiles are shared evenly by the CTAs (WorkIter): a CTA's share covers the end of one
+// tile and the beginning of the next. Each segment's fp32 partial tile goes to a workspace (column-chunk major, so a
+// warp's 32 rows are contiguous), and per 32-row slab the LAST arriving warp (ticket counter, re-armed for the next
+// launch) adds the segments in k order — deterministic — and runs the normal epilogue on the sum; a tile that one CTA
+// covers alone takes the normal path. Round 1's split-K (row-major partials at M = 512, short k-loops) measured
+// slower and was removed; uniform k-slices per tile (first half of round 2) could not use 148 SMs for 80 tiles.
 template <int BN, bool S2, bool WS = false, bool SPLIT = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapA2,
@@ -181,11 +236,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         for (int kb = 0; kb < k_blocks; ++kb)
           tma_load_2d(b_res + kb * L::B_BYTES, &mapB, b_full, kb * BK, n_tile_fixed * BN);
       }
-      for (int t = unit; t < p.tiles_total; t += n_units) {
-        const int tile = SPLIT ? t / p.splits : t;
-        const int ks = SPLIT ? t - tile * p.splits : 0;
-        const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
-        const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
+      WorkIter<SPLIT> work(p, k_blocks, unit, n_units);
+      WorkItem wk;
+      while (work.next(p, wk)) {
+        const int tile = wk.tile, kb0 = wk.kb0, kb1 = wk.kb1;
         const int n_tile = tile % p.tiles_n;
         int m_tile = tile / p.tiles_n;
         const int x0 = (m_tile % p.tiles_x) * p.TW;
@@ -244,15 +298,15 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       mbar_wait(b_full, 0);
       tc_fence_after();
     }
-    for (int t = unit; t < p.tiles_total; t += n_units, ++it) {
+    WorkIter<SPLIT> work(p, k_blocks, unit, n_units);
+    WorkItem wk;
+    for (; work.next(p, wk); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tb + acc * L::ACC_STRIDE;
-      const int ks = SPLIT ? t % p.splits : 0;
-      const int kb0 = SPLIT ? k_blocks * ks / p.splits : 0;
-      const int kb1 = SPLIT ? k_blocks * (ks + 1) / p.splits : k_blocks;
+      const int kb0 = wk.kb0, kb1 = wk.kb1;
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
@@ -296,9 +350,12 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
     const int n_out = p.geglu ? p.N / 2 : p.N;
 
     uint32_t g = 0;  // running chunk counter -> staging buffer + barrier parity
-    int it = wg;     // index of the tile in this CTA's sequence: stage it & 1 == wg
-    for (int t = unit + wg * n_units; t < p.tiles_total; t += 2 * n_units, it += 2) {
-      const int tile = SPLIT ? t / p.splits : t;
+    int it = 0;      // index of the work item in this CTA's sequence: this warpgroup drains stage it & 1 == wg
+    WorkIter<SPLIT> work(p, k_blocks, unit, n_units);
+    WorkItem wk;
+    for (; work.next(p, wk); ++it) {
+      if ((it & 1) != wg) continue;
+      const int tile = wk.tile;
       const int n_tile = tile % p.tiles_n;
       int m_tile = tile / p.tiles_n;
       const int x0 = (m_tile % p.tiles_x) * p.TW;
@@ -311,13 +368,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       const int col_base = n_tile * out_cols_per_tile;
 
       [[maybe_unused]] const float4* part_rd = nullptr;
-      if constexpr (SPLIT) {
-        // publish this k-slice's fp32 partial tile, hand the accumulator back, take a ticket for the 32-row slab
+      if (SPLIT && wk.nsl > 1) {
+        // publish this segment's fp32 partial tile, hand the accumulator back, take a ticket for the 32-row slab
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
         const uint32_t t_part = tmem_base + acc * L::ACC_STRIDE + (static_cast<uint32_t>(q * 32) << 16);
-        const int ks = t - tile * p.splits;
-        float4* part = p.ws_partial + (static_cast<size_t>(tile) * p.splits + ks) * (BN / 4 * BM) + row;
+        if (wk.nsl > p.sk_slots) __trap();  // host / device disagree on the segment count: never corrupt silently
+        const size_t slot0 = static_cast<size_t>(tile - p.sk_first) * p.sk_slots;
+        float4* part = p.ws_partial + (slot0 + wk.slice) * (BN / 4 * BM) + row;
         for (int c = 0; c < BN / 32; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(t_part + c * 32, r);
@@ -334,14 +392,14 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         int last = 0;
         if (lane == 0) {
           mbar_arrive(&tmem_empty[acc]);
-          unsigned int* tk = p.ws_tickets + tile * 4 + q;
-          last = atomicAdd(tk, 1u) == static_cast<unsigned int>(p.splits - 1);
+          unsigned int* tk = p.ws_tickets + (tile - p.sk_first) * 4 + q;
+          last = atomicAdd(tk, 1u) == static_cast<unsigned int>(wk.nsl - 1);
           if (last) *tk = 0u;  // re-arm for the next launch
         }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (!last) continue;
         __threadfence();
-        part_rd = p.ws_partial + static_cast<size_t>(tile) * p.splits * (BN / 4 * BM) + row;
+        part_rd = p.ws_partial + slot0 * (BN / 4 * BM) + row;
       }
 
       // prefetch residual slabs for the first two chunks (their buffers are free: at most one store
@@ -359,7 +417,7 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
         __syncwarp();
       }
 
-      if constexpr (!SPLIT) {
+      if (part_rd == nullptr) {
         mbar_wait(&tmem_full[acc], acc_phase);
         tc_fence_after();
       }
@@ -406,11 +464,11 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
 
         float v[32];
         if (!p.geglu) {
-          if constexpr (SPLIT) {
-            // slices in slice order (fixed summation order whichever CTA arrived last); L2-coherent, coalesced loads
+          if (SPLIT && part_rd != nullptr) {
+            // segments in k order (fixed summation order whichever CTA arrived last); L2-coherent, coalesced loads
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
-            for (int sl = 0; sl < p.splits; ++sl) {
+            for (int sl = 0; sl < wk.nsl; ++sl) {
               const float4* src = part_rd + static_cast<size_t>(sl) * (BN / 4 * BM) + static_cast<size_t>(c * 8) * BM;
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
@@ -557,10 +615,10 @@ gemm_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant
       }
       if (p.stats_out != nullptr && ln == 0 && x0 + lx < p.rows_total)
         p.stats_out[static_cast<size_t>(x0 + lx) * p.tiles_n + n_tile] = make_float2(st_sum, st_sq);
-      // accumulator fully read -> hand the TMEM stage back to the MMA warp (SPLIT: already done above)
+      // accumulator fully read -> hand the TMEM stage back to the MMA warp (published segments: already done above)
       tc_fence_before();
       __syncwarp();
-      if (!SPLIT && lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (part_rd == nullptr && lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
     if (lane == 0) tma_store_wait_all0();
   }
@@ -672,33 +730,70 @@ static int pick_bn(int N, int M_tiles, bool geglu) {
   return best;
 }
 
-// The scheduling decision for one problem: pixel tile shape, tile width, weight-stationary or streaming.
+// The scheduling decision for one problem: pixel tile shape, tile width, weight-stationary or streaming, stream-K.
 struct GemmPlan {
   int TW, TH, TN, tiles_m;
   int bn;
-  bool ws;     // weight-stationary 128-wide tiles (grid must then be a multiple of the column-tile count)
-  int splits;  // k-slices per tile (needs a workspace)
+  bool ws;       // weight-stationary 128-wide tiles (grid must then be a multiple of the column-tile count)
+  int sk_first;  // stream-K (needs a workspace): tiles [sk_first, tiles) are shared k-block-wise by sk_ctas CTAs
+  int sk_ctas;   // 0: no stream-K
+  int sk_slots;
 };
 
 constexpr int64_t SPLITK_TICKET_BYTES = 4096 * sizeof(unsigned int);
 constexpr int SPLITK_BN = 64;
-// Split-K pays when few tiles run long k-loops: a CTA moves one k-block per ~0.1 us whatever the tile width, and the
-// fix-up (fp32 partial tile out, splits tiles back in through L2, ticket) costs about as much as 16 + 4 * splits of them.
-static int pick_splits(int tiles, int k_blocks, int64_t ws_bytes) {
+
+static int streamk_mode() {  // MVD_STREAMK: 0 = off, 1 = launches smaller than the machine only, 2 (default) = + tails
+  static const int v = [] {
+    const char* e = getenv("MVD_STREAMK");
+    return e == nullptr ? 2 : atoi(e);
+  }();
+  return v;
+}
+
+// Stream-K for the part of a launch that does not fill the machine: the last, partial wave of `rem` tiles (or all tiles
+// of a launch with fewer tiles than SMs). Whole tiles would keep `rem` SMs busy for k_blocks k-block steps; sharing
+// the rem * k_blocks units evenly keeps every SM busy for `per` steps, at the price of the partial exchange (an fp32
+// tile out per segment, `slots` of them back in through L2 for the segment that arrives last, a ticket). Costs are in
+// k-block steps of a 64-wide tile: a step moves 16 KB of A and bn / 8 KB of B into the SM (the K-long launches this is
+// for are L2->SM bound: profiles/r1_tma_bw.txt), a tile has ~16 steps of fixed cost, the exchange 8 + 3 per slot and
+// 64 columns (fitted to profiles/r2_streamk_time.txt, where the model picks the fastest width at every shape).
+struct StreamK {
+  int first, ctas, slots;
+  double cost;  // of the whole launch
+};
+static StreamK eval_streamk(int tiles, int k_blocks, int bn, int64_t ws_bytes) {
   const int sms = sm_count();
-  if (ws_bytes <= SPLITK_TICKET_BYTES || tiles * 2 > sms || tiles > 1024) return 1;
-  int best = 1;
-  double best_cost = k_blocks;
-  for (int sp = 2; sp <= 8; ++sp) {
-    if (tiles * sp > sms || k_blocks / sp < 16) break;
-    if (SPLITK_TICKET_BYTES + static_cast<int64_t>(tiles) * sp * BM * SPLITK_BN * 4 > ws_bytes) break;
-    const double cost = static_cast<double>((k_blocks + sp - 1) / sp) + 16.0 + 4.0 * sp;
-    if (cost < best_cost * 0.8) {
-      best_cost = cost;
-      best = sp;
-    }
+  const double w = (16.0 + bn / 8.0) / 24.0;
+  const int first = tiles / sms * sms;
+  const int rem = tiles - first;
+  StreamK r{tiles, 0, 0, (first / sms) * k_blocks * w + 16.0 + (rem > 0 ? k_blocks * w : 0.0)};
+  const int mode = streamk_mode();
+  if (rem == 0 || mode <= 0 || ws_bytes <= SPLITK_TICKET_BYTES || (first > 0 && mode < 2)) return r;
+  const int units = rem * k_blocks;
+  constexpr int kMinUnits = 12;  // k-block steps per CTA below which the fixed costs dominate
+  const int ctas = units / kMinUnits < sms ? units / kMinUnits : sms;
+  if (ctas <= rem || static_cast<int64_t>(units) * ctas >= (1LL << 31)) return r;
+  const int per = (units + ctas - 1) / ctas;
+  // segments per tile, exactly as WorkIter assigns them (CTA i owns units [floor(i T / G), floor((i + 1) T / G)))
+  int slots = 1;
+  for (int t = 0; t < rem; ++t) {
+    const int c_first = ((t * k_blocks + 1) * ctas - 1) / units;
+    const int c_last = ((t * k_blocks + k_blocks) * ctas - 1) / units;
+    if (c_last - c_first + 1 > slots) slots = c_last - c_first + 1;
   }
-  return best;
+  if (rem * 4 > static_cast<int>(SPLITK_TICKET_BYTES / sizeof(unsigned int)) ||
+      SPLITK_TICKET_BYTES + static_cast<int64_t>(rem) * slots * BM * bn * 4 > ws_bytes)
+    return r;
+  const double whole = k_blocks * w + 16.0;
+  const double shared = per * w + 16.0 + 8.0 + 3.0 * slots * (bn / 64.0);
+  if (shared < 0.85 * whole) {
+    r.first = first;
+    r.ctas = ctas;
+    r.slots = slots;
+    r.cost = (first / sms) * k_blocks * w + shared;
+  }
+  return r;
 }
 static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, int stride, int geglu, int force_bn,
                           bool two_source, int64_t ws_bytes = 0) {
@@ -712,14 +807,28 @@ static GemmPlan plan_gemm(int Nimg, int H, int W, int Cin, int Cout, int ntaps, 
           (force_bn == 0 || force_bn == 128) && (!geglu || force_bn == 128) && !two_source &&
           Cout / 128 <= sm_count() && pl.tiles_m * (Cout / 128) >= 4 * sm_count();
   if (pl.ws) pl.bn = 128;
-  pl.splits = 1;
-  if (!pl.ws && !geglu && stride == 1 && (force_bn == 0 || force_bn == SPLITK_BN)) {
-    const int tiles64 = ((Cout + SPLITK_BN - 1) / SPLITK_BN) * pl.tiles_m;
-    const int sp = pick_splits(tiles64, ntaps * (Cin / 64), ws_bytes);
-    if (sp > 1) {
-      pl.splits = sp;
-      pl.bn = SPLITK_BN;
+  auto tiles_of = [&](int bn) { return ((Cout + bn - 1) / bn) * pl.tiles_m; };
+  pl.sk_first = tiles_of(pl.bn);
+  pl.sk_ctas = pl.sk_slots = 0;
+  if (!pl.ws && !geglu && stride == 1) {
+    const int k_blocks = ntaps * (Cin / 64);
+    StreamK best = eval_streamk(tiles_of(pl.bn), k_blocks, pl.bn, ws_bytes);
+    // launches of less than two waves of 64-wide tiles: with the k-blocks shared, wave quantisation no longer favours
+    // narrow tiles, so the width is chosen again by the cost of the whole launch
+    if (force_bn == 0 && ws_bytes > SPLITK_TICKET_BYTES && streamk_mode() > 0 && tiles_of(64) < 2 * sm_count()) {
+      const int cands[3] = {64, 128, 160};
+      best.cost = 1e30;
+      for (int i = 0; i < 3; ++i) {
+        const StreamK c = eval_streamk(tiles_of(cands[i]), k_blocks, cands[i], ws_bytes);
+        if (c.cost < best.cost) {
+          best = c;
+          pl.bn = cands[i];
+        }
+      }
     }
+    pl.sk_first = best.first;
+    pl.sk_ctas = best.ctas;
+    pl.sk_slots = best.slots;
   }
   return pl;
 }
@@ -784,12 +893,15 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   g.tiles_n = (Cout + BN - 1) / BN;
   g.tiles_total = g.tiles_n * tiles_m;
   g.rows_total = W;
-  g.splits = pl.splits;
-  if (pl.splits > 1) {
+  g.sk_first = g.tiles_total;
+  if (pl.sk_ctas > 0) {
     MVD_CHECK((reinterpret_cast<uintptr_t>(ex->workspace) & 15) == 0, "gemm: workspace must be 16-byte aligned");
     g.ws_tickets = static_cast<unsigned int*>(ex->workspace);
     g.ws_partial = reinterpret_cast<float4*>(static_cast<char*>(ex->workspace) + SPLITK_TICKET_BYTES);
-    g.tiles_total *= pl.splits;  // work items: (tile, k-slice), slice fastest
+    g.sk_first = pl.sk_first;
+    g.sk_ctas = pl.sk_ctas;
+    g.sk_slots = pl.sk_slots;
+    g.sk_units = (g.tiles_total - pl.sk_first) * ntaps * (Cin / 64);
   }
   if (ex != nullptr) {
     const bool linear_mode = ntaps == 1 && H == 1 && Nimg == 1;
@@ -885,13 +997,28 @@ static int run_gemm_conv(const OperandA& a1, const OperandA* a2, const void* w, 
   }
 
   if (pl.ws) return launch_ws(mA, mA2, mB, mO, mR, g, stream);
-  if (pl.splits > 1) {
-    using L = SmemLayout<SPLITK_BN>;
-    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<SPLITK_BN, false, false, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
-    const int grid = g.tiles_total < sm_count() ? g.tiles_total : sm_count();
-    MVD_CUDA(launch_pdl(gemm_conv_kernel<SPLITK_BN, false, false, true>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL,
-                        stream, mA, mA2, mB, mO, mR, g));
+  if (pl.sk_ctas > 0) {
+    // whole-tile work (if any) is spread over every SM; a launch that is stream-K only needs just its CTAs
+    const int grid = pl.sk_first > 0 ? sm_count() : pl.sk_ctas;
+#define MVD_LAUNCH_SK(bn)                                                                                             \
+  case bn: {                                                                                                          \
+    using L = SmemLayout<bn>;                                                                                         \
+    MVD_CUDA(cudaFuncSetAttribute(gemm_conv_kernel<bn, false, false, true>,                                           \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));                            \
+    MVD_CUDA(launch_pdl(gemm_conv_kernel<bn, false, false, true>, dim3(grid), dim3(GEMM_THREADS), L::TOTAL, stream,   \
+                        mA, mA2, mB, mO, mR, g));                                                                     \
+    break;                                                                                                            \
+  }
+    switch (BN) {
+      MVD_LAUNCH_SK(64)
+      MVD_LAUNCH_SK(128)
+      MVD_LAUNCH_SK(160)
+      MVD_LAUNCH_SK(256)
+      default:
+        set_error("gemm/conv: unsupported tile width %d", BN);
+        return MVD_ERR_INVALID;
+    }
+#undef MVD_LAUNCH_SK
     MVD_CUDA(cudaGetLastError());
     count_launches(1);
     return MVD_OK;

@@ -41,6 +41,9 @@ def _rows2d(t: torch.Tensor, name: str):
 
 # split-K of under-filled GEMM / conv launches (csrc/gemm.cu); MVD_SPLIT_K=0 switches it off for A/B runs
 SPLIT_K = os.environ.get("MVD_SPLIT_K", "1") != "0"
+# launches of at least one wave of attention units run as persistent CTAs (csrc/attn.cu); they own the machine, so the
+# two attention branches of an adapter block are then launched back to back instead of on two streams
+ATTN_PERSIST = os.environ.get("MVD_ATTN_PERSIST", "1") != "0"
 
 
 class _GemmExtras(ctypes.Structure):  # mirrors mvd_gemm_extras (include/mvd_b200.h)
@@ -86,7 +89,7 @@ def linear_column_tiles(M: int, N: int, K: int, geglu: bool = False, tile_n: int
     return got
 
 
-_GEMM_WS_FLOATS = 4 << 20  # 16 MiB of split-K scratch per (device, stream)
+_GEMM_WS_FLOATS = 16 << 20  # 64 MiB of stream-K scratch (fp32 partial tiles) per (device, stream)
 
 
 def _extras(ln: Optional["LNFold"], stats: Optional["RowStats"], film, N: int, M: int, device=None):
@@ -281,6 +284,15 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
 _ATTN_WS_BYTES = None
 
 
+ATTN_PERSIST_MAX_KV = 96 * 128  # csrc/attn.cu ATT_PERSIST_MAX_BLOCKS
+
+
+def attention_is_persistent(batch: int, heads: int, s_q: int, s_kv: int, sms: int) -> bool:
+    """Mirror of the launcher's choice (csrc/attn.cu): at least one wave of 256-row units, two-tile kernel, items of at
+    most ATT_PERSIST_MAX_BLOCKS KV blocks -> one persistent CTA per SM that owns the machine for the launch."""
+    return ATTN_PERSIST and s_q >= 512 and s_kv <= ATTN_PERSIST_MAX_KV and attention_units(batch, heads, s_q) >= sms
+
+
 def attention_units(batch: int, heads: int, s_q: int) -> int:
     """Scheduling units (256-row tile pair, head, batch) of an attention launch — the `co_units` of its sibling."""
     return ((s_q + 255) // 256) * heads * batch
@@ -470,6 +482,15 @@ def conv_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor) -> torch.Tens
     out = torch.empty((n, 4, H, W), device=x.device, dtype=F32)
     check(lib().mvd_conv_out_bf16_f32(_p(x), _p(w), _p(bias), _p(out), n, H, W, cin, _stream()),
           "mvd_conv_out_bf16_f32")
+    return out
+
+
+def head4_to_nchw(x: torch.Tensor) -> torch.Tensor:
+    """x: NHWC bf16 [N,H,W,C>=4] -> fp32 NCHW [N,4,H,W] of its first 4 channels (the tail of the 32-column conv_out)."""
+    _contig(x, "x")
+    n, H, W, C = x.shape
+    out = torch.empty((n, 4, H, W), device=x.device, dtype=F32)
+    check(lib().mvd_head4_to_nchw_f32(_p(x), C, _p(out), n, H * W, _stream()), "mvd_head4_to_nchw_f32")
     return out
 
 

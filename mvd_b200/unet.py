@@ -126,6 +126,9 @@ def _bf16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
     return t.detach().to(BF16).contiguous()
 
 
+CONV_OUT_TENSOR_CORES = os.environ.get("MVD_CONV_OUT_TC", "1") != "0"
+
+
 class LNInput:
     """A LayerNorm to be folded into the GEMM that consumes it: the module (gamma, beta, eps) + the row statistics of
     the raw activation, produced by the epilogue of the launch that wrote it (ops.RowStats)."""
@@ -640,11 +643,20 @@ class UNet2DConditionModel(PackedModule):
         return dict(
             w_in=_bf16(self.conv_in.weight.permute(0, 2, 3, 1)), b_in=_bf16(self.conv_in.bias),
             w_out=_bf16(self.conv_out.weight.permute(0, 2, 3, 1)), b_out=_bf16(self.conv_out.bias),
+            # conv_out as a 32-column tcgen05 conv: the 4 weight rows [(ky,kx,c) order] zero-padded to the narrowest tile
+            w_out32=self._pad_rows(_bf16(self.conv_out.weight.permute(0, 2, 3, 1)).reshape(self.conv_out.out_channels, -1), 32),
+            b_out32=self._pad_rows(_bf16(self.conv_out.bias), 32),
             g_out=_bf16(self.conv_norm_out.weight), bn_out=_bf16(self.conv_norm_out.bias),
             # all 22 time_emb_proj layers as one skinny GEMM
             tw=_bf16(torch.cat([r.time_emb_proj.weight for r in res], 0)),
             tb=_bf16(torch.cat([r.time_emb_proj.bias for r in res], 0)), toffs=offs,
         )
+
+    @staticmethod
+    def _pad_rows(t: torch.Tensor, rows: int) -> torch.Tensor:
+        out = torch.zeros((rows,) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+        out[: t.shape[0]].copy_(t)
+        return out
 
     def timestep_rows(self, t: torch.Tensor, bsz: int):
         """diffusers Timesteps + TimestepEmbedding, then all 22 time_emb_proj(SiLU(temb)) as one skinny GEMM:
@@ -691,7 +703,11 @@ class UNet2DConditionModel(PackedModule):
             skips = skips[:-n]
         hn = ops.groupnorm(nhwc_view(h), p["g_out"], p["bn_out"], self.config.norm_num_groups, self.config.norm_eps,
                            silu=True)
-        out = ops.conv_out(hn, p["w_out"], p["b_out"])
+        if CONV_OUT_TENSOR_CORES and self.conv_out.out_channels == 4 and hn.shape[-1] % 64 == 0:
+            # 8 x 64 x 64 x 320 -> 4: 120 us as a CUDA-core kernel, 16 us as a 32-column implicit GEMM + the 4-channel tail
+            out = ops.head4_to_nchw(ops.conv3x3(hn, p["w_out32"], bias=p["b_out32"]))
+        else:
+            out = ops.conv_out(hn, p["w_out"], p["b_out"])
         return UNetOut((out,))
 
 

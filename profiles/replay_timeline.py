@@ -14,7 +14,7 @@ from torch.profiler import ProfilerActivity, profile
 import bench
 from mvd_b200 import dist as mdist
 
-shard_of = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+shard_of = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 1
 dev = "cuda:0"
 torch.cuda.set_device(0)
 sp = mdist.shard_plan(bench.VIEWS, bench.CFG, shard_of, 0)
@@ -59,3 +59,12 @@ print(f"shard_of={shard_of}: {len(ev) // steps} kernels/step, wall {wall / steps
 print(f"{'kernel':44s} {'n/step':>7s} {'us/step':>9s} {'avg us':>8s}")
 for k, v in sorted(busy.items(), key=lambda kv: -kv[1]):
     print(f"{k[:44]:44s} {count[k] / steps:7.1f} {v / steps:9.1f} {v / count[k]:8.2f}")
+
+if "--list" in sys.argv:  # every kernel of the LAST replayed step: start (us from the step's first kernel), duration
+    per = len(ev) // steps
+    last = ev[-per:]
+    base = last[0].time_range.start
+    print(f"\nlast step, {per} kernels: start_us dur_us name")
+    for e in last:
+        name = e.name.split("(")[0].replace("void mvd::", "").replace("mvd::", "")
+        print(f"{(e.time_range.start - base):9.1f} {(e.time_range.end - e.time_range.start):8.1f} {name[:60]}")

@@ -192,6 +192,16 @@ def test_conv_in_out():
     out = ops.conv_out(x, w.permute(0, 2, 3, 1).contiguous(), b)
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1)
     _close(out, ref, "conv_out", atol=1e-3, rtol=1e-3)
+    # the route the model takes: 32-column tcgen05 conv (4 weight rows zero-padded) + the 4-channel fp32 NCHW tail
+    w32 = torch.zeros(32, 9 * 320, device="cuda", dtype=torch.bfloat16)
+    w32[:4] = w.permute(0, 2, 3, 1).reshape(4, -1)
+    b32 = torch.zeros(32, device="cuda", dtype=torch.bfloat16)
+    b32[:4] = b
+    full = ops.conv3x3(x, w32, bias=b32)
+    assert full[..., 4:].abs().max().item() == 0.0
+    out_tc = ops.head4_to_nchw(full)
+    assert out_tc.shape == ref.shape and out_tc.dtype == torch.float32
+    _close(out_tc, ref, "conv_out via tcgen05 conv", atol=1.6e-2, rtol=8e-3)  # one bf16 rounding of the result
 
 
 def test_layout_misc():

@@ -138,10 +138,17 @@ def test_linear_row_stats_and_layernorm_fold(M, C, N):
 
 
 @pytest.mark.parametrize("n,hw,cin,cin2,cout", [(1, 8, 1280, 0, 1280), (1, 8, 1280, 1280, 1280), (2, 8, 1280, 1280, 1280),
-                                                (1, 16, 1280, 640, 1280), (1, 16, 640, 0, 1280)])
+                                                (1, 16, 1280, 640, 1280), (1, 16, 640, 0, 1280),
+                                                (1, 32, 640, 0, 640),      # 80 tiles: every CTA's share spans 2 tiles
+                                                (1, 32, 1280, 640, 640),   # the same with two sources
+                                                (1, 64, 320, 0, 320),      # 160 tiles: one whole wave + a 12-tile tail
+                                                (2, 32, 320, 0, 640),      # 160 tiles, short k-loops
+                                                (8, 64, 320, 0, 320),      # 512 wide tiles: 3 whole waves + 68 shared
+                                                (4, 32, 640, 640, 640),
+                                                (2, 8, 640, 0, 1280)])     # 9 segments per tile at 12-13 k-blocks per CTA
 def test_conv3x3_split_k(n, hw, cin, cin2, cout):
-    """Few tiles, long k-loops (the 8x8 / 16x16 levels of a view-sharded rank): the launch is split along K, the fp32
-    partial tiles are summed in slice order by the last-arriving CTA. Same result as the fp32 reference, bit-identical
+    """Launches (or last waves) that do not fill the machine share their k-blocks evenly over the CTAs (stream-K): the
+    fp32 partial tiles are summed in k order by the last-arriving CTA. Same result as the fp32 reference, bit-identical
     across launches, ticket counters re-armed; the planner reports the un-split plan without a workspace."""
     from mvd_b200 import ops
 
@@ -157,13 +164,50 @@ def test_conv3x3_split_k(n, hw, cin, cin2, cout):
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
 
 
-def test_linear_split_k_long_k():
+@pytest.mark.parametrize("M,K,N", [(64, 5120, 1280),     # ff.net[2] at the 8x8 level of one sample
+                                   (4096, 1280, 320),    # ff.net[2] at 64x64 of one sample: 160 tiles, 20 k-blocks
+                                   (1024, 2560, 640),    # 80 tiles, 40 k-blocks
+                                   (32768, 1280, 320),   # 512 wide tiles: whole waves + shared tail
+                                   (200, 1280, 1280)])   # ragged rows
+def test_linear_split_k_long_k(M, K, N):
     from mvd_b200 import ops
 
-    M, K, N = 64, 5120, 1280  # ff.net[2] at the 8x8 level of one sample
     a, w, b, r = _randn(M, K, seed=1), _randn(N, K, scale=K ** -0.5, seed=2), _randn(N, seed=3), _randn(M, N, seed=4)
-    out = ops.linear(a, w, bias=b, residual=r)
-    _cmp(out, a.float() @ w.float().t() + b.float() + r.float(), "linear split-K 64x5120x1280", atol=3e-2)
+    outs = [ops.linear(a, w, bias=b, residual=r).clone() for _ in range(2)]
+    _cmp(outs[0], a.float() @ w.float().t() + b.float() + r.float(), f"linear stream-K {M}x{K}x{N}", atol=3e-2)
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_stream_k_shape_sweep():
+    """Every CTA count / segment layout the planner can produce for small launches: M, N, K swept so that the number
+    of tiles, k-blocks per CTA and segments per tile all vary (a wrong slot bound corrupts the neighbouring tile)."""
+    from mvd_b200 import ops
+
+    bad = []
+    for M in (64, 128, 200, 384, 640, 1024, 1536):
+        for N in (320, 640, 1280):
+            for K in (640, 1280, 2560, 5760):
+                a, w = _randn(M, K, seed=M + K), _randn(N, K, scale=K ** -0.5, seed=N + K)
+                out = ops.linear(a, w)
+                ref = a.float() @ w.float().t()
+                err = (out.float() - ref).abs().max().item()
+                if not err <= 3e-2 * max(1.0, ref.abs().max().item()):
+                    bad.append((M, N, K, err))
+    assert not bad, bad
+
+
+def test_stream_k_matches_whole_tile_schedule(monkeypatch):
+    """The same launch with and without the workspace (stream-K on / off): both within bf16 rounding of each other."""
+    from mvd_b200 import ops
+
+    x = _randn(1, 32, 32, 640, seed=1)
+    w9 = _randn(640, 9 * 640, scale=(9 * 640) ** -0.5, seed=2)
+    b = _randn(640, seed=3)
+    on = ops.conv3x3(x, w9, bias=b)
+    monkeypatch.setattr(ops, "SPLIT_K", False)
+    off = ops.conv3x3(x, w9, bias=b)
+    d = (on.float() - off.float()).abs().max().item()
+    assert d <= 2e-2 * max(1.0, off.float().abs().max().item()), d  # one bf16 rounding step of the largest value
 
 
 def test_film_epilogue_linear_and_conv():
