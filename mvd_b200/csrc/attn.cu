@@ -753,7 +753,7 @@ attn_pair_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant
 // item boundary: q_empty (all QK of an item retired -> its Q buffer may be refilled) and o_free (the epilogue has
 // read O_t from TMEM -> PV_t(0) of the next item may overwrite it).
 // ================================================================================================
-constexpr int ATT3_SMEM = (4 + 2 * ATT2_KS) * ATT_TILE_BYTES + 1024 + 1024;
+constexpr int ATT3_SMEM = (4 + 2 * ATT2_KS + 2) * ATT_TILE_BYTES + 1024 + 1024;  // Q x2, K/V ring, O staging
 constexpr int ATT_PERSIST_MAX_BLOCKS = 96;  // KV blocks per item up to which the persistent form is used
 
 struct PairItem {
@@ -779,17 +779,18 @@ __device__ __forceinline__ PairItem pair_item(const PairSched& sc, int skv, int 
   return w;
 }
 
-template <int POLY8>
+template <int POLY8, bool TRACE = false>
 __global__ void __launch_bounds__(ATT2_THREADS, 1)
 attn_pair_persist_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-                         const __grid_constant__ CUtensorMap mapV, const AttnArgs p, const PairSched sc,
-                         const int n_items) {
+                         const __grid_constant__ CUtensorMap mapV, const __grid_constant__ CUtensorMap mapO,
+                         const AttnArgs p, const PairSched sc, const int n_items, long long* trace = nullptr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;  // two buffers of two tiles
   uint8_t* sK = smem + 4 * ATT_TILE_BYTES;
   uint8_t* sV = sK + ATT2_KS * ATT_TILE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ATT2_KS * ATT_TILE_BYTES);
+  uint8_t* sO = sV + ATT2_KS * ATT_TILE_BYTES;  // [2 tiles][4 warps][32 rows x 128 B], 128B-swizzled, for the TMA store
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * ATT_TILE_BYTES);
   uint64_t* q_full = bars;                   // [2] per Q buffer
   uint64_t* q_empty = bars + 2;              // [2]
   uint64_t* k_full = bars + 4;               // [KS]
@@ -813,6 +814,7 @@ attn_pair_persist_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapV);
+    tma_prefetch_desc(&mapO);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&q_full[b], 1);
       mbar_init(&q_empty[b], 1);
@@ -983,13 +985,18 @@ attn_pair_persist_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_
     const uint32_t t_o = tmem_base + tm2_o(t) + lane_off;
     uint32_t g = 0;
     int it = 0;
+    // item-boundary stamps of CTA 0, per tile: trace[(t * 8 + it) * 8 + {0 item start, 1 first S ready, 2 block loop
+    // done, 3 O final, 4 stored}]
+    const bool tracer = TRACE && blockIdx.x == 0 && q == 0 && lane == 0;
     for (int idx = blockIdx.x; idx < n_items; idx += n_ctas, ++it) {
       const PairItem w = pair_item(sc, p.Skv, idx);
       float m_ref = -INFINITY;
       float l = 0.f;
+      if (tracer && it < 8) trace[(t * 8 + it) * 8 + 0] = clock64();
       for (int j = 0; j < w.n_blocks; ++j, ++g) {
         mbar_wait(&s_full[t], g & 1);
         tc_fence_after();
+        if (tracer && it < 8 && j == 0) trace[(t * 8 + it) * 8 + 1] = clock64();
         float x[ATT_BN];
         {
           uint32_t* xr = reinterpret_cast<uint32_t*>(x);
@@ -1077,8 +1084,10 @@ attn_pair_persist_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_
       }
 
       // ---- epilogue of the item
+      if (tracer && it < 8) trace[(t * 8 + it) * 8 + 2] = clock64();
       mbar_wait(&o_final[t], it & 1);
       tc_fence_after();
+      if (tracer && it < 8) trace[(t * 8 + it) * 8 + 3] = clock64();
       float o[ATT_D];
       {
         uint32_t* orr = reinterpret_cast<uint32_t*>(o);
@@ -1145,11 +1154,15 @@ attn_pair_persist_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_
           }
         }
       }
-      const int row = w.q_pair * 256 + row_in_unit;
-      if (store && row < p.Sq) {
+      // The warp's 32 rows x 64 bf16 go out as ONE TMA store from a swizzled staging slab. (Storing 16 bytes per lane
+      // to 32 different rows cost ~2000 cycles of LSU back-pressure per item: profiles/r2_attn_trace.txt.) Rows >= S_q
+      // are clipped by the tensor map.
+      if (store) {
         const float inv_l = 1.f / l;
-        __nv_bfloat16* dst = p.out + static_cast<int64_t>(w.batch) * p.o_batch_stride +
-                             static_cast<int64_t>(row) * p.ldo + w.head * ATT_D;
+        uint8_t* slab = sO + (t * 4 + q) * 4096;
+        if (lane == 0) tma_store_wait_read0();  // the previous item's store has finished reading the slab
+        __syncwarp();
+        uint8_t* rowp = slab + lane * 128;
 #pragma unroll
         for (int c = 0; c < ATT_D; c += 8) {
           uint4 v;
@@ -1157,10 +1170,18 @@ attn_pair_persist_kernel(const __grid_constant__ CUtensorMap mapQ, const __grid_
           v.y = pack_bf16x2(o[c + 2] * inv_l, o[c + 3] * inv_l);
           v.z = pack_bf16x2(o[c + 4] * inv_l, o[c + 5] * inv_l);
           v.w = pack_bf16x2(o[c + 6] * inv_l, o[c + 7] * inv_l);
-          *reinterpret_cast<uint4*>(dst + c) = v;
+          *reinterpret_cast<uint4*>(rowp + (((c >> 3) ^ (lane & 7)) << 4)) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&mapO, slab, w.head * ATT_D, w.q_pair * 256 + t * 128 + q * 32, w.batch);
+          tma_store_commit();
         }
       }
+      if (tracer && it < 8) trace[(t * 8 + it) * 8 + 4] = clock64();
     }
+    if (lane == 0) tma_store_wait_all0();
   }
 
   tc_fence_before();
@@ -1299,15 +1320,32 @@ extern "C" int mvd_attention_bf16_ws(const void* q, int64_t ldq, int64_t q_batch
     }();
     // (long items amortise the per-item costs by themselves, and measured slower in this form: configs[3]'s 576-block
     // reference attention 2.20 vs 2.09 ms, step 125.5 vs 122.1 ms)
-    if (persist_on && !trace && units >= sms && n_blocks <= ATT_PERSIST_MAX_BLOCKS) {
+    if (persist_on && units >= sms && n_blocks <= ATT_PERSIST_MAX_BLOCKS) {
       const int n_items = static_cast<int>(grid.x);
       const dim3 pgrid(n_items < sms ? n_items : sms);
+      CUtensorMap mO;  // output rows, one warp slab (32 rows x 64 columns) per store
+      {
+        const uint64_t dims[3] = {static_cast<uint64_t>(heads) * ATT_D, static_cast<uint64_t>(s_q),
+                                  static_cast<uint64_t>(batch)};
+        const uint64_t strides[2] = {static_cast<uint64_t>(ldo) * 2, static_cast<uint64_t>(o_batch_stride) * 2};
+        const uint32_t box[3] = {ATT_D, 32, 1};
+        if (int e = make_tmap_bf16(&mO, out, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B)) return e;
+      }
+      if (trace) {
+        MVD_CUDA(cudaFuncSetAttribute(attn_pair_persist_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      ATT3_SMEM));
+        MVD_CUDA(launch_pdl(attn_pair_persist_kernel<0, true>, pgrid, dim3(ATT2_THREADS), ATT3_SMEM, st, mQ, mK, mV, mO,
+                            a, sc, n_items, trace));
+        MVD_CUDA(cudaGetLastError());
+        count_launches(1);
+        return MVD_OK;
+      }
 #define MVD_PAIR_P(POLY)                                                                                                \
   do {                                                                                                                  \
     MVD_CUDA(cudaFuncSetAttribute(attn_pair_persist_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,          \
                                   ATT3_SMEM));                                                                          \
-    MVD_CUDA(launch_pdl(attn_pair_persist_kernel<POLY>, pgrid, dim3(ATT2_THREADS), ATT3_SMEM, st, mQ, mK, mV, a, sc,    \
-                        n_items));                                                                                      \
+    MVD_CUDA(launch_pdl(attn_pair_persist_kernel<POLY>, pgrid, dim3(ATT2_THREADS), ATT3_SMEM, st, mQ, mK, mV, mO, a,    \
+                        sc, n_items, static_cast<long long*>(nullptr)));                                                                                      \
   } while (0)
       if (poly == 1) MVD_PAIR_P(1);
       else if (poly == 2) MVD_PAIR_P(2);

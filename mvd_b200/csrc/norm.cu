@@ -14,6 +14,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
+
 #include <cooperative_groups.h>
 #include "host_common.h"
 #include "../../include/mvd_b200.h"
@@ -501,6 +505,136 @@ gn_fused_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv
   cluster.sync();  // no CTA may exit while a peer can still read its s_part
 }
 
+// Row-major cluster GroupNorm for FULL batches (>= 6 images): a cluster of CL CTAs per image, each CTA owns a range of
+// pixels with ALL channels. Unlike the group-major kernels above (4-byte accesses to 20-80-byte segments of every
+// pixel: 2.6x sector over-fetch and ~3x the instructions, ncu: issue-bound at 27 us for 8x4096x320), every access
+// here is a coalesced 16-byte vector: the slab is read from HBM once into shared memory, per-channel sums are reduced
+// per group inside the CTA, the per-group partials of the CL CTAs are combined over distributed shared memory (rank
+// order -> deterministic), then the exact centred second moment the same way, then normalise (+SiLU) and store.
+// Thread (tx, ty) = (tid % vpr, tid / vpr) owns channel octet tx of every TY-th row: fixed channels per thread.
+constexpr int GNR_UNROLL = 8;
+constexpr int GNR_MAX_THREADS = 640;
+
+__global__ void __launch_bounds__(GNR_MAX_THREADS)
+gn_rows_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
+                       int groups, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
+                       const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int CL = static_cast<int>(cluster.num_blocks());
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int C = c1 + c2;
+  const int vpr = C >> 3;  // 16-byte vectors per row
+  const int cpg = C / groups;
+  const int TY = blockDim.x / vpr;
+  const int tx = threadIdx.x % vpr, ty = threadIdx.x / vpr;
+  const int n = blockIdx.y;
+  const int rows_per = (hw + CL - 1) / CL;
+  const int r0 = rank * rows_per;
+  const int rows = (r0 + rows_per <= hw) ? rows_per : (hw > r0 ? hw - r0 : 0);
+  extern __shared__ uint4 gnr_slab[];                                       // [rows_per][vpr]
+  float* s_acc = reinterpret_cast<float*>(gnr_slab + static_cast<size_t>(rows_per) * vpr);  // [TY][C]
+  __shared__ float s_part[2][GN_MAX_GROUPS];  // this CTA's per-group partials (read by the whole cluster)
+  __shared__ float s_stat[2][GN_MAX_GROUPS];  // mean, rstd
+  const int c = tx * 8;
+  GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
+  src.base += static_cast<int64_t>(r0) * src.cs;
+  const float cnt = static_cast<float>(hw) * static_cast<float>(cpg);
+
+  // ---- pass 1: HBM -> shared memory, per-channel sums
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int r = ty; r < rows; r += TY * GNR_UNROLL) {
+    uint4 v[GNR_UNROLL];
+#pragma unroll
+    for (int u = 0; u < GNR_UNROLL; ++u) {
+      const int rr = r + u * TY;
+      v[u] = rr < rows ? *reinterpret_cast<const uint4*>(src.base + static_cast<int64_t>(rr) * src.cs) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < GNR_UNROLL; ++u) {
+      const int rr = r + u * TY;
+      if (rr < rows) {
+        gnr_slab[static_cast<size_t>(rr) * vpr + tx] = v[u];
+        float f[8];
+        unpack8(v[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+      }
+    }
+  }
+  auto reduce_groups = [&](int which) {
+    // per-channel partials of the TY row phases -> per-group partial of this CTA (fixed order), published for the cluster
+    float4* dst = reinterpret_cast<float4*>(s_acc + static_cast<size_t>(ty) * C + c);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      float t = 0.f;
+      for (int y = 0; y < TY; ++y) {
+        const float* row = s_acc + static_cast<size_t>(y) * C + threadIdx.x * cpg;
+        for (int k = 0; k < cpg; ++k) t += row[k];
+      }
+      s_part[which][threadIdx.x] = t;
+    }
+    cluster.sync();
+    if (threadIdx.x < groups) {
+      float tot = 0.f;
+      for (int r = 0; r < CL; ++r) tot += *cluster.map_shared_rank(&s_part[which][threadIdx.x], r);
+      s_stat[which][threadIdx.x] = which == 0 ? tot / cnt : rsqrtf(tot / cnt + eps);  // biased variance, as torch
+    }
+    __syncthreads();
+  };
+  reduce_groups(0);
+
+  // ---- pass 2: centred second moment from the on-chip copy
+  float mean[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    mean[k] = s_stat[0][(c + k) / cpg];
+    acc[k] = 0.f;
+  }
+  for (int r = ty; r < rows; r += TY) {
+    float f[8];
+    unpack8(gnr_slab[static_cast<size_t>(r) * vpr + tx], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float d = f[k] - mean[k];
+      acc[k] = fmaf(d, d, acc[k]);
+    }
+  }
+  reduce_groups(1);
+
+  // ---- pass 3: normalise (+SiLU), coalesced 16-byte stores
+  float a[8], b[8];
+  {
+    float gm[8], bt[8];
+    unpack8(*reinterpret_cast<const uint4*>(gamma + c), gm);
+    unpack8(*reinterpret_cast<const uint4*>(beta + c), bt);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a[k] = gm[k] * s_stat[1][(c + k) / cpg];
+      b[k] = bt[k] - mean[k] * a[k];
+    }
+  }
+  __nv_bfloat16* obase = out + (static_cast<int64_t>(n) * hw + r0) * C + c;
+#pragma unroll 2
+  for (int r = ty; r < rows; r += TY) {
+    float f[8];
+    unpack8(gnr_slab[static_cast<size_t>(r) * vpr + tx], f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      f[k] = fmaf(f[k], a[k], b[k]);
+      if (silu) f[k] = silu_fast(f[k]);
+    }
+    *reinterpret_cast<uint4*>(obase + static_cast<int64_t>(r) * C) = pack8(f);
+  }
+  cluster.sync();  // no CTA may exit while a peer can still read its s_part
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm: one warp per row, row held in registers, two-pass (exact mean, then centered variance). Each warp walks
 // rows with a grid stride and loads its next row before it reduces the current one, so a row's memory round trip
@@ -746,6 +880,70 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
       return v > GN1_MAX_SMEM ? static_cast<int64_t>(GN1_MAX_SMEM) : v;
     }();
     const int cpg = C / groups;
+    // full batches: row-major cluster kernel (one cluster of pixel-range CTAs per image), when an image's rows fit in
+    // the shared memory of its cluster and the machine can host enough clusters at once. MVD_GN_ROWS=0 disables.
+    static const bool rows_on = [] {
+      const char* e = getenv("MVD_GN_ROWS");
+      return e != nullptr && e[0] == '1';  // opt-in until validated on hardware
+    }();
+    if (rows_on && !two_kernel_only && n_img >= 6 && hw >= 256 && C / 8 <= GNR_MAX_THREADS) {
+      int cl = 16;
+      while (cl > 1 && n_img * cl > 160) cl >>= 1;
+      const int vpr = C / 8;
+      const int threads = GNR_MAX_THREADS / vpr * vpr;
+      const int rows_per = (hw + cl - 1) / cl;
+      const size_t smem = static_cast<size_t>(rows_per) * C * 2 + static_cast<size_t>(threads / vpr) * C * 4;
+      if (cl >= 4 && smem <= 200 * 1024) {
+        MVD_CUDA(cudaFuncSetAttribute(gn_rows_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MVD_CUDA(cudaFuncSetAttribute(gn_rows_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(cl, n_img);
+        cfg.blockDim = dim3(threads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        int na = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = na;
+        // how many such clusters the device can hold at once (cached per shape class): all images in one wave, or not at all
+        static std::mutex mu;
+        static std::map<std::tuple<int, int, size_t, int>, int> cache;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        int fit = 0;
+        {
+          std::lock_guard<std::mutex> lock(mu);
+          const auto key = std::make_tuple(dev, cl, smem, threads);
+          auto it = cache.find(key);
+          if (it == cache.end()) {
+            int nc = 0;
+            if (cudaOccupancyMaxActiveClusters(&nc, gn_rows_cluster_kernel, &cfg) != cudaSuccess) {
+              nc = 0;
+              cudaGetLastError();
+            }
+            it = cache.emplace(key, nc).first;
+          }
+          fit = it->second;
+        }
+        if (fit >= (n_img < 8 ? n_img : 8)) {
+          if (pdl_enabled()) {
+            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[na].val.programmaticStreamSerializationAllowed = 1;
+            ++na;
+            cfg.numAttrs = na;
+          }
+          MVD_CUDA(cudaLaunchKernelEx(&cfg, gn_rows_cluster_kernel, a1, c1, a2, c2, hw, groups, eps, silu, gm, bt, oo));
+          MVD_CUDA(cudaGetLastError());
+          count_launches(1);
+          return MVD_OK;
+        }
+      }
+    }
     const int64_t slab = static_cast<int64_t>(hw) * cpg * 2;
     // small batches: CL CTAs (a thread-block cluster) per slab so that the launch still covers the machine
     int cl = 1;

@@ -23,7 +23,12 @@ def _close(got, ref, name, atol=2e-2, rtol=1e-2):
 
 
 @pytest.mark.parametrize("n,hw,c1,c2", [(2, 4096, 320, 0), (3, 64, 1280, 1280), (2, 1024, 640, 320), (1, 256, 1280, 640),
-                                        (2, 9216, 320, 0), (1, 37, 64, 0), (1, 4096, 640, 320), (1, 16384, 320, 0), (1, 16384, 1280, 0)])
+                                        (2, 9216, 320, 0), (1, 37, 64, 0), (1, 4096, 640, 320), (1, 16384, 320, 0), (1, 16384, 1280, 0),
+                                        # full batches: the row-major cluster kernel (and its fall-backs when an image's
+                                        # rows do not fit the cluster's shared memory)
+                                        (8, 4096, 320, 0), (8, 4096, 320, 320), (8, 1024, 640, 0), (8, 1024, 1280, 640),
+                                        (8, 1024, 640, 320), (8, 256, 1280, 1280), (8, 256, 1280, 0), (6, 1000, 320, 0),
+                                        (16, 1024, 640, 0), (8, 9216, 320, 0)])
 @pytest.mark.parametrize("silu", [False, True])
 def test_groupnorm(n, hw, c1, c2, silu):
     from mvd_b200 import ops
