@@ -11,12 +11,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-
-#include <map>
-#include <mutex>
-#include <tuple>
 
 #include <cooperative_groups.h>
 #include "host_common.h"
@@ -505,20 +502,24 @@ gn_fused_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv
   cluster.sync();  // no CTA may exit while a peer can still read its s_part
 }
 
-// Row-major cluster GroupNorm for FULL batches (>= 6 images): a cluster of CL CTAs per image, each CTA owns a range of
-// pixels with ALL channels. Unlike the group-major kernels above (4-byte accesses to 20-80-byte segments of every
-// pixel: 2.6x sector over-fetch and ~3x the instructions, ncu: issue-bound at 27 us for 8x4096x320), every access
-// here is a coalesced 16-byte vector: the slab is read from HBM once into shared memory, per-channel sums are reduced
+// Window-major cluster GroupNorm for FULL batches (>= 4 images). The group-major kernels above touch 20-80-byte
+// segments of every pixel with 4-byte accesses: 2.6x sector over-fetch and ~3x the instructions (ncu at 8x4096x320:
+// issue-bound, 27 us for 6.5 us of HBM traffic). Here a cluster of CL CTAs owns a WINDOW of CW = lcm(cpg, 16) channels
+// (whole groups, 32-byte-sector aligned) of one image, each CTA a range of pixels: every access is a 16-byte vector
+// and whole sectors are used. The window's slab is read from HBM once into shared memory; per-channel sums are reduced
 // per group inside the CTA, the per-group partials of the CL CTAs are combined over distributed shared memory (rank
 // order -> deterministic), then the exact centred second moment the same way, then normalise (+SiLU) and store.
 // Thread (tx, ty) = (tid % vpr, tid / vpr) owns channel octet tx of every TY-th row: fixed channels per thread.
+// (One cluster per IMAGE with all channels needs 16-CTA clusters for the 64x64 sites; B200 hosts only 7 of those at
+// once — measured with cudaOccupancyMaxActiveClusters — so 8 images would take two waves.)
 constexpr int GNR_UNROLL = 8;
-constexpr int GNR_MAX_THREADS = 640;
+constexpr int GNR_MAX_THREADS = 320;
+constexpr int GNR_MAX_WGROUPS = 8;  // groups per window (CW / cpg)
 
 __global__ void __launch_bounds__(GNR_MAX_THREADS)
-gn_rows_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2, int hw,
-                       int groups, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
-                       const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
+gn_window_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_bfloat16* __restrict__ x2, int c2,
+                         int hw, int groups, int cw, float eps, int silu, const __nv_bfloat16* __restrict__ gamma,
+                         const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ out) {
   pdl_wait();
   pdl_launch_dependents();
   namespace cg = cooperative_groups;
@@ -526,19 +527,22 @@ gn_rows_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_
   const int CL = static_cast<int>(cluster.num_blocks());
   const int rank = static_cast<int>(cluster.block_rank());
   const int C = c1 + c2;
-  const int vpr = C >> 3;  // 16-byte vectors per row
+  const int vpr = cw >> 3;  // 16-byte vectors per row of the window
   const int cpg = C / groups;
+  const int wgroups = cw / cpg;
   const int TY = blockDim.x / vpr;
   const int tx = threadIdx.x % vpr, ty = threadIdx.x / vpr;
   const int n = blockIdx.y;
+  const int win = blockIdx.x / CL;
   const int rows_per = (hw + CL - 1) / CL;
   const int r0 = rank * rows_per;
   const int rows = (r0 + rows_per <= hw) ? rows_per : (hw > r0 ? hw - r0 : 0);
-  extern __shared__ uint4 gnr_slab[];                                       // [rows_per][vpr]
-  float* s_acc = reinterpret_cast<float*>(gnr_slab + static_cast<size_t>(rows_per) * vpr);  // [TY][C]
-  __shared__ float s_part[2][GN_MAX_GROUPS];  // this CTA's per-group partials (read by the whole cluster)
-  __shared__ float s_stat[2][GN_MAX_GROUPS];  // mean, rstd
-  const int c = tx * 8;
+  extern __shared__ uint4 gnr_slab[];                                                        // [rows_per][vpr]
+  float* s_acc = reinterpret_cast<float*>(gnr_slab + static_cast<size_t>(rows_per) * vpr);   // [TY][cw]
+  __shared__ float s_part[2][GNR_MAX_WGROUPS];  // this CTA's per-group partials (read by the whole cluster)
+  __shared__ float s_stat[2][GNR_MAX_WGROUPS];  // mean, rstd
+  const int cl0 = tx * 8;            // channel inside the window
+  const int c = win * cw + cl0;      // channel inside the tensor
   GnSrc src = gn_src(x1, c1, x2, c2, n, hw, c);
   src.base += static_cast<int64_t>(r0) * src.cs;
   const float cnt = static_cast<float>(hw) * static_cast<float>(cpg);
@@ -568,20 +572,21 @@ gn_rows_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_
   }
   auto reduce_groups = [&](int which) {
     // per-channel partials of the TY row phases -> per-group partial of this CTA (fixed order), published for the cluster
-    float4* dst = reinterpret_cast<float4*>(s_acc + static_cast<size_t>(ty) * C + c);
+    float4* dst = reinterpret_cast<float4*>(s_acc + static_cast<size_t>(ty) * cw + cl0);
     dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
     dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     __syncthreads();
-    if (threadIdx.x < groups) {
+    // warp w reduces group w: lanes stride over the TY x cpg values, fixed-order shuffle tree
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (wid < wgroups) {
       float t = 0.f;
-      for (int y = 0; y < TY; ++y) {
-        const float* row = s_acc + static_cast<size_t>(y) * C + threadIdx.x * cpg;
-        for (int k = 0; k < cpg; ++k) t += row[k];
-      }
-      s_part[which][threadIdx.x] = t;
+      const int total = TY * cpg;
+      for (int i = lane; i < total; i += 32) t += s_acc[static_cast<size_t>(i / cpg) * cw + wid * cpg + i % cpg];
+      t = warp_sum(t);
+      if (lane == 0) s_part[which][wid] = t;
     }
     cluster.sync();
-    if (threadIdx.x < groups) {
+    if (threadIdx.x < wgroups) {
       float tot = 0.f;
       for (int r = 0; r < CL; ++r) tot += *cluster.map_shared_rank(&s_part[which][threadIdx.x], r);
       s_stat[which][threadIdx.x] = which == 0 ? tot / cnt : rsqrtf(tot / cnt + eps);  // biased variance, as torch
@@ -594,7 +599,7 @@ gn_rows_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_
   float mean[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    mean[k] = s_stat[0][(c + k) / cpg];
+    mean[k] = s_stat[0][(cl0 + k) / cpg];
     acc[k] = 0.f;
   }
   for (int r = ty; r < rows; r += TY) {
@@ -608,7 +613,7 @@ gn_rows_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_
   }
   reduce_groups(1);
 
-  // ---- pass 3: normalise (+SiLU), coalesced 16-byte stores
+  // ---- pass 3: normalise (+SiLU), 16-byte stores of whole sectors
   float a[8], b[8];
   {
     float gm[8], bt[8];
@@ -616,7 +621,7 @@ gn_rows_cluster_kernel(const __nv_bfloat16* __restrict__ x1, int c1, const __nv_
     unpack8(*reinterpret_cast<const uint4*>(beta + c), bt);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      a[k] = gm[k] * s_stat[1][(c + k) / cpg];
+      a[k] = gm[k] * s_stat[1][(cl0 + k) / cpg];
       b[k] = bt[k] - mean[k] * a[k];
     }
   }
@@ -880,25 +885,49 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
       return v > GN1_MAX_SMEM ? static_cast<int64_t>(GN1_MAX_SMEM) : v;
     }();
     const int cpg = C / groups;
-    // full batches: row-major cluster kernel (one cluster of pixel-range CTAs per image), when an image's rows fit in
-    // the shared memory of its cluster and the machine can host enough clusters at once. MVD_GN_ROWS=0 disables.
+    // full batches: window-major cluster kernel (16-byte accesses to sector-aligned channel windows). MVD_GN_ROWS=0
+    // disables it.
     static const bool rows_on = [] {
       const char* e = getenv("MVD_GN_ROWS");
-      return e != nullptr && e[0] == '1';  // opt-in until validated on hardware
+      return e == nullptr || e[0] != '0';
     }();
-    if (rows_on && !two_kernel_only && n_img >= 6 && hw >= 256 && C / 8 <= GNR_MAX_THREADS) {
-      int cl = 16;
-      while (cl > 1 && n_img * cl > 160) cl >>= 1;
-      const int vpr = C / 8;
-      const int threads = GNR_MAX_THREADS / vpr * vpr;
-      const int rows_per = (hw + cl - 1) / cl;
-      const size_t smem = static_cast<size_t>(rows_per) * C * 2 + static_cast<size_t>(threads / vpr) * C * 4;
-      if (cl >= 4 && smem <= 200 * 1024) {
-        MVD_CUDA(cudaFuncSetAttribute(gn_rows_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MVD_CUDA(cudaFuncSetAttribute(gn_rows_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    // Measured (profiles/r2_gn_window.txt, 8 images): 22.8 -> 15.3 us at 4096 x 320, 18.2 -> 16.4 us at 1024 x 1280, but
+    // slower than the group-major kernel for smaller images (three cluster-wide phases of fixed latency): used from
+    // 1.3 M elements per image. MVD_GN_ROWS=2 forces it wherever it fits (tests).
+    static const bool rows_forced = [] {
+      const char* e = getenv("MVD_GN_ROWS");
+      return e != nullptr && e[0] == '2';
+    }();
+    if (rows_on && !two_kernel_only && n_img >= 4 && hw >= 64 &&
+        (rows_forced || static_cast<int64_t>(hw) * C >= 4096 * 320)) {
+      auto lcm = [](int a, int b) {
+        int x = a, y = b;
+        while (y) {
+          const int t = x % y;
+          x = y;
+          y = t;
+        }
+        return a / x * b;
+      };
+      // window = whole groups, preferably whole 32-byte sectors; cluster = fewest CTAs whose slabs fit twice per SM
+      for (int align = 16; align >= 8; align >>= 1) {
+        const int cw = lcm(cpg, align);
+        if (C % cw != 0 || cw / cpg > GNR_MAX_WGROUPS || cw / 8 > GNR_MAX_THREADS) continue;
+        const int vpr = cw / 8;
+        const int threads = GNR_MAX_THREADS / vpr * vpr;
+        const int windows = C / cw;
+        // ALL CTAs of the launch must be resident at once (a second wave costs a whole CTA latency: measured 43-60 us
+        // with 512 one-per-SM CTAs): two CTAs per SM (<= 320 threads at 86 registers, slabs <= 104 KB), at most
+        // 2 x SMs CTAs, the largest cluster that respects this (>= 32 rows per CTA)
+        int cl = 1;
+        while (cl < 8 && windows * (2 * cl) * n_img <= 2 * sm_count() && hw / (2 * cl) >= 32) cl <<= 1;
+        if (windows * cl * n_img > 2 * sm_count()) continue;
+        const size_t smem = static_cast<size_t>((hw + cl - 1) / cl) * cw * 2 + static_cast<size_t>(threads / vpr) * cw * 4;
+        if (smem > 104 * 1024) continue;
+        MVD_CUDA(cudaFuncSetAttribute(gn_window_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(cl, n_img);
+        cfg.gridDim = dim3(windows * cl, n_img);
         cfg.blockDim = dim3(threads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
@@ -908,40 +937,17 @@ int mvd_groupnorm_bf16(const void* x1, int c1, const void* x2, int c2, const voi
         attr[0].val.clusterDim.y = 1;
         attr[0].val.clusterDim.z = 1;
         int na = 1;
+        if (pdl_enabled()) {
+          attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+          attr[na].val.programmaticStreamSerializationAllowed = 1;
+          ++na;
+        }
         cfg.attrs = attr;
         cfg.numAttrs = na;
-        // how many such clusters the device can hold at once (cached per shape class): all images in one wave, or not at all
-        static std::mutex mu;
-        static std::map<std::tuple<int, int, size_t, int>, int> cache;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        int fit = 0;
-        {
-          std::lock_guard<std::mutex> lock(mu);
-          const auto key = std::make_tuple(dev, cl, smem, threads);
-          auto it = cache.find(key);
-          if (it == cache.end()) {
-            int nc = 0;
-            if (cudaOccupancyMaxActiveClusters(&nc, gn_rows_cluster_kernel, &cfg) != cudaSuccess) {
-              nc = 0;
-              cudaGetLastError();
-            }
-            it = cache.emplace(key, nc).first;
-          }
-          fit = it->second;
-        }
-        if (fit >= (n_img < 8 ? n_img : 8)) {
-          if (pdl_enabled()) {
-            attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[na].val.programmaticStreamSerializationAllowed = 1;
-            ++na;
-            cfg.numAttrs = na;
-          }
-          MVD_CUDA(cudaLaunchKernelEx(&cfg, gn_rows_cluster_kernel, a1, c1, a2, c2, hw, groups, eps, silu, gm, bt, oo));
-          MVD_CUDA(cudaGetLastError());
-          count_launches(1);
-          return MVD_OK;
-        }
+        MVD_CUDA(cudaLaunchKernelEx(&cfg, gn_window_cluster_kernel, a1, c1, a2, c2, hw, groups, cw, eps, silu, gm, bt, oo));
+        MVD_CUDA(cudaGetLastError());
+        count_launches(1);
+        return MVD_OK;
       }
     }
     const int64_t slab = static_cast<int64_t>(hw) * cpg * 2;

@@ -9,7 +9,7 @@ try:
     peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbps"]
 except Exception:
     peak = 6550.7
-print(f"MVD_GN_ROWS={os.environ.get('MVD_GN_ROWS', '1')}  (HBM peak {peak:.0f} GB/s)")
+print(f"MVD_GN_ROWS={os.environ.get('MVD_GN_ROWS', 'default')}  (HBM peak {peak:.0f} GB/s)")
 flush = torch.empty(256 << 20, device="cuda", dtype=torch.uint8)
 for (n, hw, c1, c2) in [(8, 4096, 320, 0), (8, 4096, 320, 320), (8, 4096, 640, 320), (8, 1024, 640, 0), (8, 1024, 640, 640),
                         (8, 1024, 1280, 640), (8, 256, 1280, 0), (8, 256, 1280, 1280), (8, 64, 1280, 1280)]:

@@ -1,6 +1,7 @@
 """GPU parity of the bandwidth-bound kernels against fp32 torch math on the same inputs.
 Tolerance: bf16 output rounding (rel 2^-8) on O(1) values -> atol 2e-2 unless stated."""
 import math
+import os
 
 import pytest
 import torch
@@ -269,3 +270,34 @@ def test_cfg_ddpm_step_table_matches_scalar_variant():
         ops.advance_step(step_idx, coef, t_dev)
         assert torch.equal(lat_a, lat_b), f"step {i}"
     assert step_idx.item() == 0 and t_dev.item() == float(ts[0])  # wrapped: the loop can be replayed
+
+
+def test_groupnorm_window_kernel_everywhere():
+    """The window-major cluster kernel forced at every shape it fits (MVD_GN_ROWS=2, read once per process -> its own
+    interpreter): small images, both channel-window alignments, two-source inputs."""
+    import subprocess, sys, textwrap
+
+    code = textwrap.dedent("""
+        import sys, torch, torch.nn.functional as F
+        sys.path.insert(0, %r)
+        from mvd_b200 import ops
+        g = torch.Generator(device="cuda").manual_seed(0)
+        for (n, hw, c1, c2) in [(8, 64, 1280, 1280), (8, 256, 1280, 0), (8, 1024, 640, 0), (8, 1024, 640, 320), (4, 4096, 320, 0),
+                                (16, 1024, 640, 0), (6, 1000, 320, 0), (8, 256, 640, 0), (5, 640, 64, 0)]:
+            x1 = (torch.randn(n, hw, c1, device="cuda", generator=g) + 0.3).to(torch.bfloat16)
+            x2 = (2 * torch.randn(n, hw, c2, device="cuda", generator=g)).to(torch.bfloat16) if c2 else None
+            C = c1 + c2
+            gm = (1 + 0.2 * torch.randn(C, device="cuda", generator=g)).to(torch.bfloat16)
+            bt = (0.2 * torch.randn(C, device="cuda", generator=g)).to(torch.bfloat16)
+            out = ops.groupnorm(x1, gm, bt, groups=32, eps=1e-5, silu=True, x2=x2)
+            xin = x1.float() if x2 is None else torch.cat([x1.float(), x2.float()], -1)
+            ref = F.silu(F.group_norm(xin.permute(0, 2, 1), 32, gm.float(), bt.float(), 1e-5).permute(0, 2, 1))
+            err = (out.float() - ref).abs().max().item()
+            assert err <= 2.5e-2 + 1e-2 * ref.abs().max().item(), (n, hw, c1, c2, err)
+            again = ops.groupnorm(x1, gm, bt, groups=32, eps=1e-5, silu=True, x2=x2)
+            assert torch.equal(out, again), "not deterministic"
+        print("ok")
+    """) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MVD_GN_ROWS="2")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
