@@ -248,12 +248,13 @@ class ImageCrossAttentionProcessor(nn.Module):
             else:
                 proj = proj.view(b, s, 4 * c)
                 q, k, v, q_ref = (proj[:, :, i * c:(i + 1) * c] for i in range(4))
-            # The two branches are independent until the fused out-projection. Each launch is a non-integral
-            # number of one-CTA-per-SM waves, so the reference branch is forked onto a second stream to fill the
-            # tail of the first (inside a captured step this becomes two parallel graph branches).
-            units = ops.attention_units(b, self.heads, s)
-            big = units >= _sm_count(hidden_states.device)
+            # The two branches are independent until the fused out-projection. A launch that owns the machine
+            # (persistent CTAs) is simply followed by its sibling; otherwise each launch is a non-integral number of
+            # one-CTA-per-SM waves and the reference branch is forked onto a second stream to fill the tail of the
+            # first (inside a captured step this becomes two parallel graph branches).
             sms = _sm_count(hidden_states.device)
+            units = ops.attention_units(b, self.heads, s)
+            big = units >= sms
             if not pk["is_cross"] and (ops.attention_is_persistent(b, self.heads, s, k.shape[1], sms) or
                                        ops.attention_is_persistent(b, self.heads, s, k_ref.shape[1], sms)):
                 # each launch is a persistent grid of one CTA per SM that splits its own last wave along S_kv: nothing
