@@ -77,9 +77,12 @@ int mvd_conv3x3_bf16(const void* x, int cin1, const void* x2, int cin2, const vo
  *  - FiLM on the output (src/models/camera_encoder.py:221-234 applied by the forward hooks of src/models/mvd_unet.py:
  *    354-385 to a block's output): out = v * film_scale[g][n] + film_shift[g][n], g = image (conv) or row group
  *    (linear, rows_per_group), fp32 rows of stride film_ld.
- *  - workspace: with it, a launch that would occupy less than half of the SMs with k-loops of >= 32 k-blocks (the
- *    16x16 / 8x8 UNet levels of a view-sharded rank) is split along K over the idle SMs; the fp32 partial tiles are
- *    reduced in slice order by the last-arriving CTA (deterministic). 16 MiB cover every case. */
+ *  - workspace: with it, the part of a launch that does not fill the machine — every tile of a launch with fewer tiles
+ *    than SMs (the 16x16 / 8x8 UNet levels, a view-sharded rank), or the last partial wave of a big one — shares its
+ *    k-blocks evenly over all SMs (stream-K); the fp32 partial tiles are reduced in k order by the last-arriving CTA
+ *    (deterministic), and for launches under two waves the tile width is re-chosen for the shared schedule. Launches
+ *    with ln_stats / stats_out or GEGLU ignore it. 64 MiB cover every case of the UNet; too small a buffer simply
+ *    means whole tiles. mvd_gemm_plan reports the plan WITHOUT a workspace (the one the stats_out contract refers to). */
 typedef struct mvd_gemm_extras {
   const float* ln_stats;
   const float* ln_colsum;
@@ -91,7 +94,7 @@ typedef struct mvd_gemm_extras {
   const float* film_shift;
   int film_ld;
   void* workspace;          /* optional scratch (16-byte aligned, zero-filled once, private to launches that cannot run */
-  int64_t workspace_bytes;  /* concurrently): lets launches with few tiles and long k-loops run split-K              */
+  int64_t workspace_bytes;  /* concurrently): stream-K partial tiles + tickets                                       */
 } mvd_gemm_extras;
 
 int mvd_linear_ex_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
