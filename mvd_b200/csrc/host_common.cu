@@ -22,9 +22,9 @@ void set_error(const char* fmt, ...) {
 }
 
 // Programmatic dependent launch. Measured on B200 under graph replay: with 8 samples per GPU the step is throughput
-// bound and PDL costs 3 % (13.68 vs 13.28 ms); with 1 sample per GPU (view x CFG sharded rank) the step is launch /
-// latency bound and PDL gains 5 % (5.32 vs 5.61 ms). So it is a run-time switch: MVD_PDL=0/1 forces it, otherwise the
-// caller (DenoiseSession, by its local batch) sets it with mvd_set_launch_overlap().
+// bound and PDL costs 2-3 %; with 1 sample per GPU (view x CFG sharded rank) it gained 5 % mid-round (5.32 vs 5.61 ms)
+// and loses 2 % on the final tree (stream-K / persistent kernels already cover every SM). So it is a run-time switch:
+// MVD_PDL=0/1 forces it, otherwise the caller (DenoiseSession) sets it with mvd_set_launch_overlap() — off by default.
 static std::atomic<int> g_pdl{-1};
 static int pdl_env() {
   static const int v = [] {

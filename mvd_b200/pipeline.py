@@ -253,9 +253,12 @@ class DenoiseSession:
         ops.cfg_ddpm_step_table(out, self.latents, self.noise_table, self.cfg, self.guidance, self.coef, self.step_idx)
         self.advance()
 
-    # local batches up to this many UNet samples are launch / latency bound: their kernels are launched with
-    # programmatic dependent launch (measured: +5 % at 1 sample, +1 % at 2, -3 % at 8)
-    LAUNCH_OVERLAP_MAX_BATCH = 2
+    # Local batches up to this many UNet samples launch their kernels with programmatic dependent launch. Mid-round it
+    # paid for 1-2 samples per GPU (+5 % / +1 %, -3 % at 8); with stream-K GEMMs and persistent attention every kernel
+    # already covers all SMs and the early CTAs of a dependent only get in the way: measured on the final tree
+    # 4.565 (off) vs 4.652 ms at 1 sample, 5.80 vs 5.97 at 2, 8.02 vs 8.13 at 4, 12.52 vs 12.79 at 8 -> off (0).
+    # MVD_PDL=1 still forces it on.
+    LAUNCH_OVERLAP_MAX_BATCH = 0
 
     def capture(self, warmup: int = 2):
         """Warm every cache (weight packs, reference features, K/V) eagerly, then record one step."""
