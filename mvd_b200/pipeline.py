@@ -274,7 +274,10 @@ class DenoiseSession:
         torch.cuda.synchronize()
         before = ops.kernel_launch_count()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the stream the warm-up ran on: the per-stream scratch buffers of ops.* (stream-K partials, attention
+        # and GroupNorm workspaces) then already exist — created inside the capture, their zero-fill would become a
+        # node of the graph and run on every replay (3 x 64 MiB fills = 26 us per step in the CUPTI timeline)
+        with torch.cuda.graph(self.graph, stream=side):
             self._eager_step()
         self.launches_per_step = ops.kernel_launch_count() - before
         self.latents.copy_(saved[0])
