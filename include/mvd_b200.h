@@ -112,6 +112,15 @@ int mvd_conv3x3_ex_bf16(const void* x, int cin1, const void* x2, int cin2, const
 int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntaps, int stride, int geglu, int tile_n,
                   int* bn, int* weight_stationary, int* grid);
 
+/* The stream-K part of that decision for a plain launch that is handed `workspace_bytes` of scratch: tile width, tile
+ * and k-block counts, and the schedule — tiles [0, sk_first) are whole-tile work items, the k-blocks of tiles
+ * [sk_first, tiles) are shared by CTAs [0, sk_ctas) (CTA i owns units [floor(i T / G), floor((i + 1) T / G)) of the
+ * T = (tiles - sk_first) * k_blocks units), with sk_slots partial-tile slots per shared tile. sk_ctas = 0: no stream-K.
+ * For tests of the schedule (coverage, slot bound) without a GPU; no reference analogue. */
+int mvd_gemm_plan_streamk(int n_img, int h_out, int w_out, int c_in, int c_out, int ntaps, int stride, int tile_n,
+                          int64_t workspace_bytes, int* bn, int* tiles, int* k_blocks, int* sk_first, int* sk_ctas,
+                          int* sk_slots);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Fused flash-attention forward, head_dim 64 (tcgen05 + TMEM + TMA), csrc/attn.cu
  * ------------------------------------------------------------------------------------------------------- */

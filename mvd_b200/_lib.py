@@ -55,6 +55,7 @@ _SIGNATURES = {
     "mvd_linear_ex_bf16": (_I, [_P, _L, _I, _P, _L, _I, _P, _L, _P, _P, _I, _I, _P, _L, _P, _L, _I, _I, _I, _I, _P, _P]),
     "mvd_conv3x3_ex_bf16": (_I, [_P, _I, _P, _I, _P, _P, _P, _I, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mvd_gemm_plan": (_I, [_I] * 9 + [_P] * 3),
+    "mvd_gemm_plan_streamk": (_I, [_I] * 8 + [_L] + [_P] * 6),
     "mvd_attention_bf16": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P]),
     "mvd_attention_workspace_bytes": (_L, []),
     "mvd_attention_bf16_ws": (_I, [_P, _L, _L, _P, _L, _L, _P, _L, _L, _P, _L, _L, _I, _I, _I, _I, _F, _P, _L, _I, _P]),

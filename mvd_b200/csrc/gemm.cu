@@ -1064,6 +1064,24 @@ int mvd_gemm_plan(int n_img, int h_out, int w_out, int c_in, int c_out, int ntap
   return MVD_OK;
 }
 
+int mvd_gemm_plan_streamk(int n_img, int h_out, int w_out, int c_in, int c_out, int ntaps, int stride, int tile_n,
+                          int64_t workspace_bytes, int* bn, int* tiles, int* k_blocks, int* sk_first, int* sk_ctas,
+                          int* sk_slots) {
+  using namespace mvd;
+  MVD_CHECK(n_img > 0 && h_out > 0 && w_out > 0 && c_in > 0 && c_in % 64 == 0 && c_out > 0 && c_out % 32 == 0 &&
+                (ntaps == 1 || ntaps == 9) && (stride == 1 || stride == 2),
+            "gemm_plan: unsupported problem");
+  const GemmPlan pl = plan_gemm(n_img, h_out, w_out, c_in, c_out, ntaps, stride, /*geglu=*/0, tile_n, false,
+                                workspace_bytes);
+  if (bn) *bn = pl.bn;
+  if (tiles) *tiles = ((c_out + pl.bn - 1) / pl.bn) * pl.tiles_m;
+  if (k_blocks) *k_blocks = ntaps * (c_in / 64);
+  if (sk_first) *sk_first = pl.sk_first;
+  if (sk_ctas) *sk_ctas = pl.sk_ctas;
+  if (sk_slots) *sk_slots = pl.sk_slots;
+  return MVD_OK;
+}
+
 int mvd_linear_ex_bf16(const void* a, int64_t lda, int k1, const void* a2, int64_t lda2, int k2, const void* w,
                        int64_t ldw, const void* bias, const float* row_group_bias, int row_group_bias_ld,
                        int rows_per_group, const void* residual, int64_t ldr, void* out, int64_t ldo, int M, int N,

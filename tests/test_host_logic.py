@@ -213,3 +213,63 @@ def test_session_cfg_gating_pin_restore_and_cache_invalidation():
     assert m.invalidate_caches() >= 2
     assert "_mod_cache" not in m.camera_encoder.__dict__
     assert m.invalidate_caches() == 0
+
+
+def test_stream_k_schedule_covers_every_k_block_once():
+    """The stream-K schedule of the GEMM planner, replayed on the host exactly as the kernel's WorkIter does it
+    (csrc/gemm.cu): every k-block of every shared tile is owned by exactly one CTA, segments of a tile are numbered
+    0..nsl-1 in k order by consecutive CTAs, and no tile has more segments than the planner reserved slots for (the
+    bound that was wrong once: 9 segments for 8 slots at 2x8x8 640->1280 corrupted the neighbouring tile)."""
+    import ctypes
+
+    from mvd_b200._lib import lib
+
+    L = lib()
+    ws = 64 << 20
+    shapes = []
+    for n, hw in ((1, 8), (1, 16), (1, 32), (1, 64), (2, 8), (2, 16), (2, 32), (8, 8), (8, 16), (8, 32), (8, 64), (3, 24)):
+        for cin, cout in ((320, 320), (640, 320), (320, 640), (640, 640), (1280, 640), (1920, 640), (640, 1280),
+                          (1280, 1280), (2560, 1280), (960, 320)):
+            shapes.append((n, hw, hw, cin, cout, 9))
+    for m in (64, 128, 200, 256, 1024, 4096, 8192, 32768):
+        for k, nn in ((320, 320), (640, 320), (1280, 320), (2560, 640), (5120, 1280), (1280, 1280), (1280, 5120)):
+            shapes.append((1, 1, m, k, nn, 1))
+    used = 0
+    for (n, h, w, cin, cout, taps) in shapes:
+        o = [ctypes.c_int() for _ in range(6)]
+        assert L.mvd_gemm_plan_streamk(n, h, w, cin, cout, taps, 1, 0, ws, *[ctypes.byref(x) for x in o]) == 0
+        bn, tiles, kb, first, ctas, slots = (x.value for x in o)
+        assert kb == taps * cin // 64 and 0 <= first <= tiles
+        if ctas == 0:
+            assert first == tiles
+            continue
+        used += 1
+        rem = tiles - first
+        T = rem * kb
+        assert first % 148 == 0 and 0 < rem and rem < ctas <= 148 and T >= ctas and T * ctas < 2 ** 31
+        owner = [[] for _ in range(rem)]                       # per tile: (cta, slice, nsl, kb0, kb1)
+        for cta in range(ctas):
+            u0, u1 = cta * T // ctas, (cta + 1) * T // ctas
+            assert u1 > u0, "every stream-K CTA owns at least one k-block"
+            while u0 < u1:                                     # WorkIter::next
+                rel = u0 // kb
+                base = rel * kb
+                kb0 = u0 - base
+                ln = min(kb - kb0, u1 - u0)
+                c_first = ((base + 1) * ctas - 1) // T
+                c_last = ((base + kb) * ctas - 1) // T
+                owner[rel].append((cta, cta - c_first, c_last - c_first + 1, kb0, kb0 + ln))
+                u0 += ln
+        for rel, segs in enumerate(owner):
+            nsl = segs[0][2]
+            assert nsl <= slots, (n, h, cin, cout, rel, nsl, slots)
+            assert [s[1] for s in segs] == list(range(nsl)) and all(s[2] == nsl for s in segs)
+            assert segs[0][3] == 0 and segs[-1][4] == kb
+            assert all(a[4] == b[3] for a, b in zip(segs, segs[1:])), "k ranges of a tile must tile [0, k_blocks)"
+        ticket_words, partial_bytes = rem * 4, rem * slots * 128 * bn * 4
+        assert ticket_words <= 4096 and 4096 * 4 + partial_bytes <= ws
+    assert used >= 40, f"only {used} of {len(shapes)} shapes took the stream-K path"
+    # without a workspace nothing is shared
+    o = [ctypes.c_int() for _ in range(6)]
+    assert L.mvd_gemm_plan_streamk(1, 32, 32, 640, 640, 9, 1, 0, 0, *[ctypes.byref(x) for x in o]) == 0
+    assert o[4].value == 0 and o[3].value == o[1].value
