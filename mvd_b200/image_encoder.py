@@ -65,11 +65,25 @@ class ImageEncoder(nn.Module):
             self.dtype = kwargs["dtype"]
         return super().to(*args, **kwargs)
 
+    def _unet_params(self):
+        """The frozen UNet's parameters as a list built once (walking ~700 modules per eager call cost more than the
+        cache lookup it serves); rebuilt when Module._apply (.to / .cuda / .half) may have replaced the tensors."""
+        plist = self.__dict__.get("_plist")
+        if plist is None:
+            plist = list(self.unet.parameters())
+            self.__dict__["_plist"] = plist
+        return plist
+
+    def _apply(self, fn, *args, **kwargs):
+        self.__dict__.pop("_plist", None)
+        self.__dict__.pop("_feat_cache", None)
+        return super()._apply(fn, *args, **kwargs)
+
     def forward(self, latents, text_embeddings, timestep):
         key = None
         if self.cache:
             t_key = _key(timestep) if torch.is_tensor(timestep) else float(timestep)
-            key = (_key(latents), _key(text_embeddings), t_key, _versions(*self.unet.parameters()))
+            key = (_key(latents), _key(text_embeddings), t_key, _versions(*self._unet_params()))
             cached = self.__dict__.get("_feat_cache")
             if cached is not None and cached[0] == key:
                 self.extracted_features = cached[1]

@@ -145,7 +145,8 @@ class MultiViewUNet(nn.Module):
         return self
 
     _CACHE_KEYS = ("_pack_cache", "_ref_cache", "_gather_cache", "_ln_cache", "_ctx_cache", "_feat_cache",
-                   "_text_cache", "_shard_idx", "_rep_cache", "_xview_cache", "_emb_cache", "_mod_cache", "_film_cache")
+                   "_text_cache", "_shard_idx", "_rep_cache", "_xview_cache", "_emb_cache", "_mod_cache", "_film_cache",
+                   "_plist")
 
     def invalidate_caches(self):
         """Drop every step-invariant cache (weight packs, folded-LayerNorm packs, reference / text K/V, frozen-UNet
