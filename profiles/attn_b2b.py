@@ -5,8 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from mvd_b200 import ops
 g = torch.Generator(device="cuda").manual_seed(0)
-print(f"MVD_ATTN_PERSIST={os.environ.get('MVD_ATTN_PERSIST', '1')} MVD_ATTN_SPLIT={os.environ.get('MVD_ATTN_SPLIT', '1')} "
-      f"MVD_ATTN_STREAM={os.environ.get('MVD_ATTN_STREAM', '1')}")
+print(f"MVD_ATTN_PERSIST={os.environ.get('MVD_ATTN_PERSIST', '1')} MVD_ATTN_SPLIT={os.environ.get('MVD_ATTN_SPLIT', '1')}")
 for (B, H, S, Skv) in [(8, 5, 4096, 4096), (8, 10, 1024, 1024), (4, 5, 4096, 4096), (2, 5, 4096, 4096), (1, 5, 4096, 4096),
                        (1, 10, 1024, 1024), (2, 10, 1024, 1024), (2, 5, 9216, 73728)]:
     C = H * 64
