@@ -259,7 +259,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, sca
     B, Sq, C = q.shape
     Skv = k.shape[1]
     if k.shape[0] != B or v.shape[0] != B or v.shape[1] != Skv:
-        raise ValueError("q/k/v batch or length mismatch")
+        raise ValueError(f"q/k/v batch or length mismatch: q {tuple(q.shape)} k {tuple(k.shape)} v {tuple(v.shape)}")
     if out is None:
         out = torch.empty((B, Sq, C), device=q.device, dtype=BF16)
     _req(out, "out")
